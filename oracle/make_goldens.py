@@ -1,0 +1,144 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference modules.  Build-container only.
+
+Run:  python oracle/make_goldens.py            (needs /root/reference; never run on the GPU box)
+
+It imports ``/root/reference/models/DiT.py`` and ``/root/reference/sampler/karras_sample.py``
+through ``oracle/timm_shim`` (timm is absent from the image), loads the seeded synthetic weights of
+``oracle.dit.synthetic_state_dict`` into the reference ``DiT`` with ``strict=True`` (which also pins
+the state-dict key set and shapes), runs the reference's own ``forward`` / ``forward_with_cfg`` /
+``karras_sample`` on seeded inputs and stores inputs + outputs.  Weights are NOT stored: every test
+regenerates them from (config, seed).  The committed fixtures are what pins the oracle (and, on the
+GPU box, the CUDA path) to the reference's code.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("LFM_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "timm_shim"))
+sys.path.insert(0, REF)
+
+from oracle import dit as odit  # noqa: E402
+
+
+def _import_reference():
+    # models/__init__.py imports EDM + guided_diffusion too; those import cleanly with the shim.
+    import importlib
+
+    models = importlib.import_module("models")
+    ks = importlib.import_module("sampler.karras_sample")
+    return models, ks
+
+
+CASES = {
+    # name: (model kwargs for the reference DiT ctor, weight seed)
+    "mini_uncond": (dict(depth=2, hidden_size=256, patch_size=2, num_heads=4, img_resolution=32, in_channels=4,
+                         label_dropout=0.0, num_classes=1), 11),
+    "mini_cond": (dict(depth=2, hidden_size=256, patch_size=2, num_heads=4, img_resolution=32, in_channels=4,
+                       label_dropout=0.1, num_classes=10), 12),
+    "mini_d384": (dict(depth=3, hidden_size=384, patch_size=2, num_heads=6, img_resolution=32, in_channels=4,
+                       label_dropout=0.1, num_classes=5), 13),
+}
+FULL = {
+    "dit_l2": ("DiT-L/2", dict(img_resolution=32, in_channels=4, label_dropout=0.0, num_classes=1), 1),
+    "dit_b2": ("DiT-B/2", dict(img_resolution=32, in_channels=4, label_dropout=0.1, num_classes=1000), 1),
+}
+
+
+def build(models, kwargs, seed, factory=None):
+    from models.DiT import DiT, DiT_models
+
+    net = DiT_models[factory](**kwargs) if factory else DiT(**kwargs)
+    cfg = odit.DiTConfig(img_resolution=net.x_embedder.img_size[0], patch_size=net.patch_size,
+                         in_channels=net.in_channels, hidden_size=net.pos_embed.shape[-1], depth=len(net.blocks),
+                         num_heads=net.num_heads, label_dropout=kwargs["label_dropout"],
+                         num_classes=kwargs["num_classes"])
+    sd = odit.synthetic_state_dict(cfg, seed)
+    # the fixed table must agree with the reference's own buffer before we overwrite it
+    assert torch.allclose(sd["pos_embed"], net.pos_embed.data, atol=0, rtol=0), "pos_embed restatement differs"
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    return net, cfg
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_grad_enabled(False)
+    models, ks = _import_reference()
+    g = torch.Generator().manual_seed(1234)
+
+    for name, (kw, seed) in CASES.items():
+        net, cfg = build(models, kw, seed)
+        B = 2
+        x = torch.randn(B, 4, 32, 32, generator=g)
+        out = {"x": x, "weight_seed": np.int64(seed)}
+        for k, v in kw.items():
+            out["cfg_" + k] = np.float64(v)
+        # (a) scalar (0-d) t, y = None
+        t0 = torch.tensor(0.73)
+        out["t_scalar"] = t0
+        out["v_scalar_ynone"] = net(t0, x)
+        # (b) vector t, explicit labels
+        tv = torch.tensor([0.9, 0.15])
+        y = torch.randint(0, kw["num_classes"], (B,), generator=g)
+        out["t_vec"], out["y"] = tv, y
+        out["v_vec_y"] = net(tv, x, y)
+        if kw["num_classes"] > 1:
+            # (c) forward_with_cfg on the doubled batch (test_flow_latent.py:171-181)
+            x2 = torch.cat([x, x], 0)
+            y2 = torch.cat([y, torch.full((B,), kw["num_classes"])], 0)
+            out["y_cfg"] = y2
+            out["v_cfg_1p5"] = net.forward_with_cfg(torch.tensor([0.4] * (2 * B)), x2, y2, cfg_scale=1.5)
+            mk = dict(y=y2, cfg_scale=1.5)
+            xs = x2
+        else:
+            mk = {}
+            xs = x
+        # (d) the reference's own fixed-step samplers
+        common = dict(model_kwargs=mk, device="cpu", clip_denoised=False, sigma_min=1e-5, sigma_max=1.0,
+                      s_tmin=0.0, s_tmax=1.0, s_churn=0.0)
+        out["euler6"] = ks.karras_sample(net, xs, steps=6, sampler="euler", **common)
+        out["heun5"] = ks.karras_sample(net, xs, steps=5, sampler="heun", **common)
+        if name == "mini_uncond":
+            out["heun43"] = ks.karras_sample(net, xs, steps=43, sampler="heun", **common)  # corrector stops at i=39
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
+        print("wrote", name, {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
+
+    for name, (factory, kw, seed) in FULL.items():
+        net, cfg = build(models, kw, seed, factory)
+        B = 2
+        x = torch.randn(B, 4, 32, 32, generator=g)
+        out = {"x": x, "weight_seed": np.int64(seed)}
+        if kw["num_classes"] == 1:
+            out["t"] = torch.tensor(0.5)
+            out["v"] = net(out["t"], x)
+            out["euler3"] = ks.karras_sample(net, x, steps=3, sampler="euler", model_kwargs={}, device="cpu",
+                                             clip_denoised=False, sigma_min=1e-5, sigma_max=1.0)
+        else:
+            y = torch.randint(0, 1000, (B,), generator=g)
+            y2 = torch.cat([y, torch.full((B,), 1000)], 0)
+            out["t"] = torch.tensor([0.8] * (2 * B))
+            out["y_cfg"] = y2
+            out["v_cfg_1p5"] = net.forward_with_cfg(out["t"], torch.cat([x, x], 0), y2, cfg_scale=1.5)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
+        print("wrote", name)
+        del net
+
+    # spot values of the fixed table quoted in SURVEY.md 8(c)
+    pe = odit.pos_embed_2d(1024, 16)
+    np.savez_compressed(os.path.join(OUT, "pos_embed_spots.npz"), pe_0_1_0=pe[0, 1, 0].numpy(),
+                        pe_0_16_0=pe[0, 16, 0].numpy(), row17=pe[0, 17].numpy())
+
+
+if __name__ == "__main__":
+    main()
