@@ -1,0 +1,111 @@
+/* lfm_b200.h - C ABI of liblfm_b200.so: the B200-native latent flow-matching sampling path.
+ *
+ * Drop-in boundary for the sampling hot path of VinAIResearch/LFM.  The reference has no native code and
+ * therefore no FFI of its own; each entry point below replaces a Python call site of the reference (cited as
+ * reference-file:line) and is bound from Python with ctypes (see INTEGRATION.md for the stub a reference
+ * maintainer would add).  Plain C: pointers, sizes, int status codes.  No torch types, no C++ exceptions.
+ *
+ * Conventions
+ *  - All tensor pointers are DEVICE pointers on the ctx's device unless the name ends in _host.
+ *  - Tensors use the reference's dtype and layout: latents/velocities fp32 NCHW contiguous [B, C, H, W];
+ *    labels int64 [B]; times fp32.
+ *  - The library BORROWS caller buffers for the duration of a call; it owns its weight copy and workspace.
+ *  - Work is stream-ordered on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *  - Return value: 0 = ok, non-zero = error; lfm_last_error(ctx) (or lfm_last_error(NULL) for create
+ *    failures) returns a message.  A ctx is bound to one device and is not thread-safe.
+ */
+#ifndef LFM_B200_H
+#define LFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lfm_ctx lfm_ctx;
+
+enum { LFM_ARCH_DIT = 0 };
+enum { LFM_DTYPE_F32 = 0 };
+enum { LFM_METHOD_EULER = 0, LFM_METHOD_HEUN = 1 };
+
+/* Constructor arguments of the reference network (models/DiT.py:157-169, selected by
+ * models/__init__.py:12-17 create_network).  image side = grid * patch. */
+typedef struct lfm_model_desc {
+    int32_t arch;            /* LFM_ARCH_DIT */
+    int32_t img_resolution;  /* latent side, e.g. 32 */
+    int32_t patch_size;      /* 2 */
+    int32_t in_channels;     /* 4 */
+    int32_t hidden_size;     /* D; multiple of 128; heads * 64 */
+    int32_t depth;           /* L */
+    int32_t num_heads;       /* H; head_dim must be 64 */
+    int32_t mlp_hidden;      /* int(hidden_size * mlp_ratio) */
+    int32_t table_rows;      /* y_embedder rows = num_classes + (label_dropout > 0) (models/DiT.py:79-81) */
+} lfm_model_desc;
+
+typedef struct lfm_ode_stats {
+    int64_t nfe;       /* network evaluations */
+    int64_t accepted;  /* dopri5 accepted steps */
+    int64_t rejected;  /* dopri5 rejected steps */
+} lfm_ode_stats;
+
+/* models/__init__.py:6-17 create_network(config) -> nn.Module.  Creates an empty context on `device`. */
+int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out);
+
+/* nn.Module.load_state_dict (test_flow_latent.py:142): one call per state-dict entry, `key` exactly as in the
+ * reference state_dict; `ptr` may be a host or a device pointer (fp32).  The data is copied
+ * (GEMM weights are repacked to bf16).  Unknown key or wrong shape -> error (strict=True behaviour). */
+int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int dtype, const int64_t* shape, int ndim);
+
+/* After all parameters are set: checks that none is missing (strict), allocates the activation workspace for
+ * up to `max_batch` network rows (2x images under CFG) and builds the TMA descriptors. */
+int lfm_finalize(lfm_ctx* ctx, int max_batch);
+
+/* model(t, x, y) / model.forward_with_cfg(t, x, y, cfg_scale)  (models/DiT.py:252-272, 274-290).
+ *   t: [t_numel] fp32, t_numel == 1 (0-d t, broadcast) or B.   x, v_out: [B, C, H, W].   y: [B] int64 or NULL
+ *   (NULL = the table's last row, models/DiT.py:259-260).
+ *   cfg_scale <= 1: v_out = DiT(t, x, y).
+ *   cfg_scale  > 1: forward_with_cfg - B must be even, rows [B/2, B) of y hold the null class; the first half
+ *   of x is evaluated with both label halves and v_out = cat[g, g], g = u + s (c - u). */
+int lfm_forward(lfm_ctx* ctx, const float* t, int t_numel, const float* x, const int64_t* y, int B, float cfg_scale,
+                float* v_out, void* stream);
+
+/* Fixed-step integration of dx/dt = v(t, x) over the nodes t_grid[0..n_grid) (device or host pointer, fp32):
+ *   LFM_METHOD_EULER  x += v(t_i, x) (t_{i+1} - t_i)                sampler/karras_sample.py:86-118 and
+ *                                                                   torchdiffeq fixed-grid euler (test_flow_latent.py:61-73)
+ *   LFM_METHOD_HEUN   predictor + trapezoid corrector for intervals i < heun_corrector_limit, Euler beyond
+ *                                                                   sampler/karras_sample.py:122-161
+ *   t_as_vector: 0 = the model sees a 0-d t (torchdiffeq), 1 = a [B] vector (Karras samplers).
+ *   x_inout: [B_img, C, H, W] latents, updated in place.  y: labels, [B_img] (cfg_scale <= 1) or [2*B_img]
+ *   (cfg_scale > 1: conditional labels then null labels; a 2*B_img-row network batch is evaluated per NFE).
+ *   The whole trajectory runs from a captured CUDA graph; no host synchronisation between steps. */
+int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const float* t_grid_host, int n_grid, int t_as_vector,
+                     int heun_corrector_limit, const int64_t* y, int B_img, float cfg_scale, lfm_ode_stats* stats,
+                     void* stream);
+
+/* Adaptive Dormand-Prince 5(4) from t0 down to t1 with torchdiffeq's controller (rtol/atol, RMS norm over the
+ * whole batch, fp64 time, dense output at t1)        test_flow_latent.py:42-76 with --method dopri5. */
+int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double t1, double rtol, double atol, const int64_t* y,
+                      int B_img, float cfg_scale, lfm_ode_stats* stats, void* stream);
+
+const char* lfm_last_error(const lfm_ctx* ctx);
+void lfm_destroy(lfm_ctx* ctx);
+
+/* Number of kernels the library has launched on this ctx since creation (bench.py's gpu_launches). */
+int64_t lfm_launch_count(const lfm_ctx* ctx);
+
+/* ---- kernel-level entry points used by the parity tests (tests/test_gpu_kernels.py) ------------------- */
+/* C = A[M,K] W[N,K]^T with epilogue `epi` (0 bias->bf16, 1 bias+gelu->bf16, 2 gated residual fp32, 3 bias->fp32).
+ * a, w: bf16 device pointers.  block_n: 128 or 256. */
+int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float* bias, void* out, const float* gate,
+                 int gate_stride, int rows_per_sample, int M, int N, int K, int epi, int block_n, void* stream);
+/* softmax(q k^T / 8) v on a [B*256, 3*D] bf16 qkv buffer -> out [B*256, D] bf16.  variant: 0 = P in TMEM,
+ * 1 = P through shared memory.  dbg_s (optional) receives the raw S = q k^T as fp32 [B, H, 256, 256]. */
+int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, int H, int variant, float* dbg_s, void* stream);
+/* Intermediate activations of the last lfm_forward (fp32 token stream [B*T, D] after all blocks). */
+int lfm_dbg_tokens(lfm_ctx* ctx, float* out, int B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFM_B200_H */

@@ -1,0 +1,406 @@
+// lfm_b200 - the non-GEMM kernels of the DiT velocity network and the ODE-solver arithmetic.
+// All HBM- or latency-bound; plain CUDA cores, vectorised, coalesced.  fp32 everywhere except the bf16 tensors
+// that feed the tcgen05 GEMMs.
+#pragma once
+#include "common.cuh"
+
+namespace lfm {
+
+// ------------------------------------------------------------------------------------------------
+// K2: sinusoidal timestep features  tf[b, :] = [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(1e4) i / 128)
+// (reference models/DiT.py:43-62; raw t in [0,1], cos first).  t_numel == 1 broadcasts.
+__global__ void timestep_features_kernel(const float* __restrict__ t, int t_numel, float* __restrict__ tf, int B) {
+    const int b = blockIdx.x;
+    const int i = threadIdx.x;  // 0..255
+    if (b >= B) return;
+    const float tv = t[t_numel == 1 ? 0 : b];
+    const int k = i & 127;
+    const float freq = expf(-9.210340371976184f * static_cast<float>(k) / 128.0f);
+    const float a = tv * freq;
+    tf[b * 256 + i] = (i < 128) ? cosf(a) : sinf(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2/K3: skinny linear  out[b, j] = act( bias[j] + sum_k W[j, k] in[b, k] (+ table[idx[b], j]) )
+// One warp per output feature j; the weight row stays in registers while the warp sweeps the batch.
+// MODE 0: SiLU -> fp32 out          (t_embedder.mlp.0 + SiLU)
+// MODE 1: + label-embedding row, then SiLU -> bf16 out (c = t_emb + y_emb; adaLN's leading SiLU, DiT.py:125,264)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ in, int B,
+                     int N, int K, const float* __restrict__ table, const long long* __restrict__ idx, int null_row,
+                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+    constexpr int MAXV = 9;  // K <= 1152
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= N) return;
+    const int nv = K / 128;  // float4 per lane
+    float4 w[MAXV];
+#pragma unroll
+    for (int m = 0; m < MAXV; ++m)
+        if (m < nv) w[m] = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(j) * K) + m * 32 + lane);
+    const float bj = bias[j];
+    for (int b = 0; b < B; ++b) {
+        const float4* ip = reinterpret_cast<const float4*>(in + static_cast<size_t>(b) * K);
+        float acc = 0.f;
+#pragma unroll
+        for (int m = 0; m < MAXV; ++m) {
+            if (m < nv) {
+                const float4 x = __ldg(ip + m * 32 + lane);
+                acc = fmaf(w[m].x, x.x, acc);
+                acc = fmaf(w[m].y, x.y, acc);
+                acc = fmaf(w[m].z, x.z, acc);
+                acc = fmaf(w[m].w, x.w, acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float v = acc + bj;
+            if (MODE == 1) {
+                const long long row = (idx != nullptr) ? idx[b] : static_cast<long long>(null_row);
+                v += table[static_cast<size_t>(row) * N + j];
+            }
+            v = silu(v);
+            if (MODE == 0)
+                out_f32[static_cast<size_t>(b) * N + j] = v;
+            else
+                out_bf16[static_cast<size_t>(b) * N + j] = __float2bfloat16(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: patch embed (timm PatchEmbed conv k=p, s=p as a 16-wide dot product) + bias + pos_embed -> fp32 tokens.
+// x is NCHW fp32 with x_rows samples; network row b reads sample (b % x_rows) (CFG duplicates the latents,
+// reference models/DiT.py:279-280).  p = 2, C = 4 => patch vector (c, p, q) of 16 floats.
+// One block = 8 tokens; thread d handles features d, d+256, ...
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const float* __restrict__ x, int x_rows, const float* __restrict__ W /*[D,16]*/,
+                   const float* __restrict__ bias, const float* __restrict__ pos /*[T,D]*/, float* __restrict__ tok,
+                   int D, int G /*grid side*/, int C, int M) {
+    __shared__ float patch[8][16];
+    const int T = G * G, HW = 2 * G;
+    const int m0 = blockIdx.x * 8;
+    if (threadIdx.x < 128) {
+        const int tk = threadIdx.x >> 4, e = threadIdx.x & 15;
+        const int m = m0 + tk;
+        if (m < M) {
+            const int b = (m / T) % x_rows, t = m % T;
+            const int gh = t / G, gw = t % G;
+            const int c = e >> 2, p = (e >> 1) & 1, q = e & 1;
+            patch[tk][e] = x[((static_cast<size_t>(b) * C + c) * HW + (2 * gh + p)) * HW + 2 * gw + q];
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += 256) {
+        float w[16];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(d) * 16) + v);
+            w[4 * v] = w4.x, w[4 * v + 1] = w4.y, w[4 * v + 2] = w4.z, w[4 * v + 3] = w4.w;
+        }
+        const float bd = bias[d];
+#pragma unroll
+        for (int tk = 0; tk < 8; ++tk) {
+            const int m = m0 + tk;
+            if (m < M) {
+                float acc = bd;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc = fmaf(w[e], patch[tk][e], acc);
+                tok[static_cast<size_t>(m) * D + d] = acc + __ldg(pos + static_cast<size_t>(m % T) * D + d);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5/K9: LayerNorm (no affine, eps 1e-6) + adaLN modulate, fp32 tokens -> bf16 GEMM operand.
+//   y = (x - mean) * rstd * (1 + scale[b]) + shift[b]        (reference models/DiT.py:20-21,119,121,129-130)
+// One warp per token row; the row lives in registers (D <= 1536).
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ shift,
+                   const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M, int D) {
+    constexpr int MAXV = 12;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= M) return;
+    const int nv = D / 128;
+    const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int m = 0; m < MAXV; ++m) {
+        if (m < nv) {
+            v[m] = xp[m * 32 + lane];
+            s += (v[m].x + v[m].y) + (v[m].z + v[m].w);
+        }
+    }
+    const float mean = warp_sum(s) / static_cast<float>(D);
+    float ss = 0.f;
+#pragma unroll
+    for (int m = 0; m < MAXV; ++m) {
+        if (m < nv) {
+            const float a = v[m].x - mean, b = v[m].y - mean, c = v[m].z - mean, d = v[m].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + 1e-6f);
+    const size_t boff = static_cast<size_t>(row / rows_per_sample) * mod_stride;
+    const float4* shp = reinterpret_cast<const float4*>(shift + boff);
+    const float4* scp = reinterpret_cast<const float4*>(scale + boff);
+    uint2* yp = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int m = 0; m < MAXV; ++m) {
+        if (m < nv) {
+            const float4 sh = __ldg(shp + m * 32 + lane), sc = __ldg(scp + m * 32 + lane);
+            const float a = fmaf((v[m].x - mean) * rstd, 1.f + sc.x, sh.x);
+            const float b = fmaf((v[m].y - mean) * rstd, 1.f + sc.y, sh.y);
+            const float c = fmaf((v[m].z - mean) * rstd, 1.f + sc.z, sh.z);
+            const float d = fmaf((v[m].w - mean) * rstd, 1.f + sc.w, sh.w);
+            yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11: FinalLayer (LN + modulate + Linear(D, p*p*C)) + unpatchify, fp32 (reference models/DiT.py:134-149,230-243).
+// Out-feature order of the linear is (p, q, c) -> pixel (c, 2h+p, 2w+q).  One warp per token; the 16 x D weight
+// sits in shared memory.  Writes v_net[b, c, :, :] (NCHW fp32).
+__global__ void __launch_bounds__(256)
+final_layer_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
+                   int mod_stride, const float* __restrict__ W /*[16, D]*/, const float* __restrict__ bias,
+                   float* __restrict__ v_net, int M, int D, int G, int C) {
+    extern __shared__ float sW[];  // [16][D]
+    constexpr int MAXV = 12;
+    const int P = 4 * C;  // p*p*C outputs (p = 2)
+    for (int i = threadIdx.x; i < P * D / 4; i += blockDim.x)
+        reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(W) + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nv = D / 128, T = G * G, HW = 2 * G;
+    for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+        const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+        float4 v[MAXV];
+        float s = 0.f;
+#pragma unroll
+        for (int m = 0; m < MAXV; ++m)
+            if (m < nv) {
+                v[m] = xp[m * 32 + lane];
+                s += (v[m].x + v[m].y) + (v[m].z + v[m].w);
+            }
+        const float mean = warp_sum(s) / static_cast<float>(D);
+        float ss = 0.f;
+#pragma unroll
+        for (int m = 0; m < MAXV; ++m)
+            if (m < nv) {
+                const float a = v[m].x - mean, b = v[m].y - mean, c = v[m].z - mean, d = v[m].w - mean;
+                ss += (a * a + b * b) + (c * c + d * d);
+            }
+        const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + 1e-6f);
+        const int bidx = row / T, t = row % T;
+        const size_t boff = static_cast<size_t>(bidx) * mod_stride;
+        const float4* shp = reinterpret_cast<const float4*>(shift + boff);
+        const float4* scp = reinterpret_cast<const float4*>(scale + boff);
+#pragma unroll
+        for (int m = 0; m < MAXV; ++m)
+            if (m < nv) {
+                const float4 sh = __ldg(shp + m * 32 + lane), sc = __ldg(scp + m * 32 + lane);
+                v[m].x = fmaf((v[m].x - mean) * rstd, 1.f + sc.x, sh.x);
+                v[m].y = fmaf((v[m].y - mean) * rstd, 1.f + sc.y, sh.y);
+                v[m].z = fmaf((v[m].z - mean) * rstd, 1.f + sc.z, sh.z);
+                v[m].w = fmaf((v[m].w - mean) * rstd, 1.f + sc.w, sh.w);
+            }
+        const int gh = t / G, gw = t % G;
+        for (int j = 0; j < P; ++j) {
+            const float4* wp = reinterpret_cast<const float4*>(sW + static_cast<size_t>(j) * D);
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < MAXV; ++m)
+                if (m < nv) {
+                    const float4 w4 = wp[m * 32 + lane];
+                    acc = fmaf(w4.x, v[m].x, acc);
+                    acc = fmaf(w4.y, v[m].y, acc);
+                    acc = fmaf(w4.z, v[m].z, acc);
+                    acc = fmaf(w4.w, v[m].w, acc);
+                }
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                const int p = j / (2 * C), q = (j / C) & 1, c = j % C;
+                v_net[((static_cast<size_t>(bidx) * C + c) * HW + (2 * gh + p)) * HW + 2 * gw + q] = acc + bias[j];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K12: classifier-free-guidance combine (reference models/DiT.py:285-290): rows [0,n) conditional, [n,2n) null.
+//   g = u + s (c - u).   dup != 0 also writes g into the second half (the reference returns cat[g, g]).
+__global__ void cfg_combine_kernel(const float* __restrict__ v_net, float* __restrict__ out, size_t n_half, float s,
+                                   int dup) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_half) return;
+    const float c = v_net[i], u = v_net[i + n_half];
+    const float g = u + s * (c - u);
+    out[i] = g;
+    if (dup) out[i + n_half] = g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K13: fixed-step solver updates.  The step schedule lives in device memory (t_grid) and the step index in
+// a device counter, so one captured CUDA graph serves every step of a trajectory with no host involvement.
+struct StepState {
+    int step;         // current interval index i
+    int n_intervals;  // len(t_grid) - 1
+};
+
+// Writes the model time(s) for the next evaluation: t_eval[0] = t_grid[step + which] (which: 0 = t_cur, 1 = t_next)
+__global__ void step_time_kernel(const float* __restrict__ t_grid, const StepState* __restrict__ st, int which,
+                                 float* __restrict__ t_eval) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) t_eval[0] = t_grid[st->step + which];
+}
+
+// Euler:  x <- x + v * (sign * (t[i+1] - t[i]))      (karras_sample.py:116-117; torchdiffeq y0 + dt*f with the
+// reversed-time sign folded in: there dt = s[i+1]-s[i] = -(t[i+1]-t[i]) and f = -v, the same product)
+// advance != 0 bumps the device step counter (done by thread 0 of block 0 AFTER reading it - every block reads
+// the counter before any block can finish, because the increment happens in a separate tiny kernel).
+__global__ void euler_update_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ t_grid,
+                                    const StepState* __restrict__ st, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float dt = t_grid[st->step + 1] - t_grid[st->step];
+    x[i] = x[i] + v[i] * dt;
+}
+
+// Heun predictor: x_pred = x + dt * d_cur (x itself is kept)     (karras_sample.py:152)
+__global__ void heun_predict_kernel(const float* __restrict__ x, const float* __restrict__ d_cur,
+                                    float* __restrict__ x_pred, const float* __restrict__ t_grid,
+                                    const StepState* __restrict__ st, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float dt = t_grid[st->step + 1] - t_grid[st->step];
+    x_pred[i] = x[i] + dt * d_cur[i];
+}
+
+// Heun corrector: x <- x + dt * (0.5 d_cur + 0.5 d_prime) if step < corrector_limit else x <- x_pred
+// (karras_sample.py:155-159; the guard `i < steps - 1` with the reference's never-overridden default steps = 40)
+__global__ void heun_correct_kernel(float* __restrict__ x, const float* __restrict__ d_cur,
+                                    const float* __restrict__ d_prime, const float* __restrict__ x_pred,
+                                    const float* __restrict__ t_grid, const StepState* __restrict__ st,
+                                    int corrector_limit, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int step = st->step;
+    if (step < corrector_limit) {
+        const float dt = t_grid[step + 1] - t_grid[step];
+        x[i] = x[i] + dt * (0.5f * d_cur[i] + 0.5f * d_prime[i]);
+    } else {
+        x[i] = x_pred[i];
+    }
+}
+
+__global__ void step_advance_kernel(StepState* st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) st->step += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K14: dopri5 arithmetic (torchdiffeq rk_common).  k[j] are the 7 stage derivatives.
+struct RkPtrs {
+    const float* k[7];
+};
+
+// y_out = y0 + sum_j (coef[j]) * k[j],  coef already multiplied by dt (fp32) on the host
+__global__ void rk_combine_kernel(const float* __restrict__ y0, RkPtrs kp, int nk, const float* __restrict__ coef,
+                                  float* __restrict__ y_out, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int j = 0; j < nk; ++j) acc = fmaf(kp.k[j][i], coef[j], acc);
+    y_out[i] = y0[i] + acc;
+}
+
+// partial[blk] = sum over this block's elements of ((a - b) / (atol + rtol * max(|y0|, |y1|)))^2
+// a == nullptr: a = sum_j coef[j] * k[j] (the embedded error estimate).  b may be nullptr.  Warp-shuffle reduce.
+constexpr int kRmsBlocks = 128;
+__global__ void __launch_bounds__(256)
+rms_ratio_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, RkPtrs kp,
+                         const float* __restrict__ coef, const float* __restrict__ y0, const float* __restrict__ y1,
+                         float atol, float rtol, size_t n, double* __restrict__ partial) {
+    __shared__ double wsum[8];
+    double acc = 0.0;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float num;
+        if (a != nullptr) {
+            num = a[i] - (b != nullptr ? b[i] : 0.f);
+        } else {
+            num = 0.f;
+            for (int j = 0; j < 7; ++j) num = fmaf(kp.k[j][i], coef[j], num);
+        }
+        const float tol = atol + rtol * fmaxf(fabsf(y0[i]), fabsf(y1[i]));
+        const float r = num / tol;
+        acc += static_cast<double>(r) * static_cast<double>(r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        partial[blockIdx.x] = t;
+    }
+}
+// out[0] = sqrt(sum(partial) / n)   (fixed summation order => deterministic)
+__global__ void rms_finalize_kernel(const double* __restrict__ partial, int nblk, size_t n, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < nblk; ++i) t += partial[i];
+        out[0] = static_cast<float>(sqrt(t / static_cast<double>(n)));
+    }
+}
+
+// dense-output quartic of the last accepted step evaluated at x in [0,1] (torchdiffeq _interp_fit/_interp_evaluate)
+__global__ void dopri_interp_kernel(const float* __restrict__ y0, const float* __restrict__ y1, RkPtrs kp,
+                                    const float* __restrict__ coef_mid /*dt * c_mid*/, float dt, float xq,
+                                    float* __restrict__ out, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float mid = 0.f;
+    for (int j = 0; j < 7; ++j) mid = fmaf(kp.k[j][i], coef_mid[j], mid);
+    const float a0 = y0[i], a1 = y1[i], ym = a0 + mid, f0 = kp.k[0][i], f1 = kp.k[6][i];
+    const float ca = 2.f * dt * (f1 - f0) - 8.f * (a1 + a0) + 16.f * ym;
+    const float cb = dt * (5.f * f0 - 3.f * f1) + 18.f * a0 + 14.f * a1 - 32.f * ym;
+    const float cc = dt * (f1 - 4.f * f0) - 11.f * a0 - 5.f * a1 + 16.f * ym;
+    const float cd = dt * f0;
+    float total = a0 + xq * cd;
+    float xp = xq * xq;
+    total += xp * cc;
+    xp *= xq;
+    total += xp * cb;
+    xp *= xq;
+    total += xp * ca;
+    out[i] = total;
+}
+
+__global__ void axpy_kernel(const float* __restrict__ y, const float* __restrict__ f, float h, float* __restrict__ out,
+                            size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = y[i] + h * f[i];
+}
+__global__ void negate_kernel(float* __restrict__ v, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = -v[i];
+}
+
+// fp32 -> bf16 weight repack (nn.Linear weights are already [N, K] K-major: a plain cast)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+    const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(in + i);
+        *reinterpret_cast<uint2*>(out + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    } else {
+        for (size_t j = i; j < n; ++j) out[j] = __float2bfloat16(in[j]);
+    }
+}
+
+}  // namespace lfm

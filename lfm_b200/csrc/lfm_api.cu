@@ -1,0 +1,936 @@
+// lfm_b200 - C ABI (include/lfm_b200.h): context, parameter upload, DiT forward, ODE solvers.
+// Single translation unit; build:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared ...
+#include "../../include/lfm_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace lfm;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+
+static thread_local std::string g_last_error;
+
+struct lfm_ctx;
+static int fail(lfm_ctx* ctx, const char* fmt, ...);
+
+#define CUDA_OK(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor encoding through the driver entry point (no -lcuda link dependency)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Row-major bf16 matrix [rows, cols]; box = 64 columns (one 128-byte swizzle row) x box_rows rows.
+static bool make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel launch helpers
+
+static int g_num_sms = 0;
+
+template <int BN, int EPI>
+static cudaError_t launch_gemm_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                                    const GemmEpi& ep) {
+    static bool attr_set = false;
+    auto kern = gemm_bf16_tcgen05<BN, EPI>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tiles = ((M + kGemmBlockM - 1) / kGemmBlockM) * ((N + BN - 1) / BN);
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                               int epi, int block_n, const GemmEpi& ep) {
+#define LFM_GEMM_CASE(BN, E) \
+    if (block_n == BN && epi == E) return launch_gemm_inst<BN, E>(s, ta, tb, M, N, K, ep);
+    LFM_GEMM_CASE(256, EPI_BIAS_BF16)
+    LFM_GEMM_CASE(256, EPI_BIAS_GELU_BF16)
+    LFM_GEMM_CASE(256, EPI_GATE_RESID_F32)
+    LFM_GEMM_CASE(256, EPI_BIAS_F32)
+    LFM_GEMM_CASE(128, EPI_BIAS_BF16)
+    LFM_GEMM_CASE(128, EPI_BIAS_GELU_BF16)
+    LFM_GEMM_CASE(128, EPI_GATE_RESID_F32)
+    LFM_GEMM_CASE(128, EPI_BIAS_F32)
+#undef LFM_GEMM_CASE
+    return cudaErrorInvalidValue;
+}
+
+template <bool P_TMEM>
+static cudaError_t launch_attention_inst(cudaStream_t s, const CUtensorMap& tq, const CUtensorMap& tkv,
+                                         __nv_bfloat16* out, int B, int H, int D, float* dbg_s) {
+    static bool attr_set = false;
+    auto kern = attention_t256_d64<P_TMEM>;
+    if (!attr_set) {
+        cudaError_t e =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<P_TMEM>());
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e), head_dim = 64
+    kern<<<dim3(2, H, B), kAttnThreads, attn_smem_bytes<P_TMEM>(), s>>>(tq, tkv, out, D, scale_log2e, dbg_s);
+    return cudaGetLastError();
+}
+
+static inline unsigned blocks_for(size_t n, int threads = 256) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------
+// context
+
+struct ParamSlot {
+    void* dst = nullptr;        // device destination (fp32 or bf16)
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+    bool to_bf16 = false;
+    bool set = false;
+};
+
+struct BlockW {
+    __nv_bfloat16 *w_qkv, *w_proj, *w_fc1, *w_fc2;
+    float *b_qkv, *b_proj, *b_fc1, *b_fc2;
+    CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
+};
+
+struct lfm_ctx {
+    lfm_model_desc d{};
+    int device = 0;
+    int D = 0, L = 0, H = 0, T = 0, G = 0, C = 0, Hd = 0, Nmod = 0, HW = 0, chw = 0;
+    int max_rows = 0;
+    bool finalized = false;
+    std::string err;
+    int64_t launches = 0;
+    int attn_variant = 0;  // 0 = P in TMEM, 1 = P via smem
+    int bn_qkv = 256, bn_proj = 256, bn_fc1 = 256, bn_fc2 = 256, bn_mod = 256;
+
+    std::unordered_map<std::string, ParamSlot> params;
+    std::vector<void*> allocs;
+    float* staging = nullptr;
+    size_t staging_elems = 0;
+
+    // parameters
+    float *pos = nullptr, *pe_w = nullptr, *pe_b = nullptr, *t_w0 = nullptr, *t_b0 = nullptr, *t_w2 = nullptr,
+          *t_b2 = nullptr, *ytable = nullptr, *fin_w = nullptr, *fin_b = nullptr, *b_mod = nullptr;
+    __nv_bfloat16* w_mod = nullptr;
+    CUtensorMap tm_wmod;
+    std::vector<BlockW> blk;
+
+    // workspace
+    float *x_tok = nullptr, *mod = nullptr, *tfreq = nullptr, *h1 = nullptr, *v_net = nullptr;
+    __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hmid = nullptr, *c_silu = nullptr;
+    CUtensorMap tm_xn, tm_attn, tm_hmid, tm_csilu, tm_qkv_q, tm_qkv_kv;
+
+    // solver state
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    float *x_state = nullptr, *x_pred = nullptr, *v_eff = nullptr, *d_prime = nullptr, *t_grid = nullptr,
+          *t_eval = nullptr, *coef = nullptr, *ratio = nullptr, *y_stage = nullptr;
+    float* kbuf[7] = {nullptr};
+    double* partial = nullptr;
+    long long* y_buf = nullptr;
+    StepState* step_state = nullptr;
+    float* ratio_host = nullptr;  // pinned
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+    };
+    std::map<std::string, StepGraph> graphs;
+};
+
+static int fail(lfm_ctx* ctx, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx != nullptr) ctx->err = buf;
+    return 1;
+}
+
+template <typename Tp>
+static int dev_alloc(lfm_ctx* ctx, Tp** p, size_t count) {
+    void* q = nullptr;
+    CUDA_OK(cudaMalloc(&q, count * sizeof(Tp) + 256));
+    CUDA_OK(cudaMemset(q, 0, count * sizeof(Tp) + 256));
+    ctx->allocs.push_back(q);
+    *p = static_cast<Tp*>(q);
+    return 0;
+}
+
+static void add_param(lfm_ctx* ctx, const std::string& key, void* dst, std::vector<int64_t> shape, bool to_bf16) {
+    ParamSlot s;
+    s.dst = dst;
+    s.shape = shape;
+    s.numel = 1;
+    for (int64_t v : shape) s.numel *= static_cast<size_t>(v);
+    s.to_bf16 = to_bf16;
+    ctx->params[key] = s;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v != nullptr && *v != 0) ? atoi(v) : dflt;
+}
+
+extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out) {
+    lfm_ctx* ctx = nullptr;
+    if (desc == nullptr || out == nullptr) return fail(nullptr, "lfm_create: null argument");
+    if (desc->arch != LFM_ARCH_DIT) return fail(nullptr, "lfm_create: unsupported arch %d", desc->arch);
+    if (desc->patch_size != 2) return fail(nullptr, "lfm_create: only patch_size 2 is implemented (got %d)", desc->patch_size);
+    if (desc->img_resolution != 32)
+        return fail(nullptr, "lfm_create: only 32x32 latents (256 tokens) are implemented (got %d)", desc->img_resolution);
+    if (desc->hidden_size % 128 != 0 || desc->hidden_size > 1536)
+        return fail(nullptr, "lfm_create: hidden_size must be a multiple of 128 and <= 1536 (got %d)", desc->hidden_size);
+    if (desc->num_heads * 64 != desc->hidden_size)
+        return fail(nullptr, "lfm_create: head_dim must be 64 (hidden %d, heads %d)", desc->hidden_size, desc->num_heads);
+    if (desc->mlp_hidden % 64 != 0) return fail(nullptr, "lfm_create: mlp_hidden must be a multiple of 64");
+    if (desc->in_channels != 4) return fail(nullptr, "lfm_create: in_channels must be 4");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, "lfm_create: no CUDA device (liblfm_b200 has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, "lfm_create: bad device %d", device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(nullptr, "lfm_create: device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+    ctx = new lfm_ctx();
+    ctx->d = *desc;
+    ctx->device = device;
+    CUDA_OK(cudaSetDevice(device));
+    g_num_sms = prop.multiProcessorCount;
+    ctx->D = desc->hidden_size;
+    ctx->L = desc->depth;
+    ctx->H = desc->num_heads;
+    ctx->G = desc->img_resolution / desc->patch_size;
+    ctx->T = ctx->G * ctx->G;
+    ctx->C = desc->in_channels;
+    ctx->Hd = desc->mlp_hidden;
+    ctx->HW = desc->img_resolution;
+    ctx->chw = ctx->C * ctx->HW * ctx->HW;
+    ctx->Nmod = (6 * ctx->L + 2) * ctx->D;
+    ctx->attn_variant = env_int("LFM_ATTN_VARIANT", 0);
+    const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
+
+    if (dev_alloc(ctx, &ctx->pos, (size_t)T * D)) return 1;
+    if (dev_alloc(ctx, &ctx->pe_w, (size_t)D * 16)) return 1;
+    if (dev_alloc(ctx, &ctx->pe_b, D)) return 1;
+    if (dev_alloc(ctx, &ctx->t_w0, (size_t)D * 256)) return 1;
+    if (dev_alloc(ctx, &ctx->t_b0, D)) return 1;
+    if (dev_alloc(ctx, &ctx->t_w2, (size_t)D * D)) return 1;
+    if (dev_alloc(ctx, &ctx->t_b2, D)) return 1;
+    if (dev_alloc(ctx, &ctx->ytable, (size_t)desc->table_rows * D)) return 1;
+    if (dev_alloc(ctx, &ctx->fin_w, (size_t)16 * D)) return 1;
+    if (dev_alloc(ctx, &ctx->fin_b, 16)) return 1;
+    if (dev_alloc(ctx, &ctx->w_mod, (size_t)ctx->Nmod * D)) return 1;
+    if (dev_alloc(ctx, &ctx->b_mod, ctx->Nmod)) return 1;
+    add_param(ctx, "pos_embed", ctx->pos, {1, T, D}, false);
+    add_param(ctx, "x_embedder.proj.weight", ctx->pe_w, {D, 4, 2, 2}, false);
+    add_param(ctx, "x_embedder.proj.bias", ctx->pe_b, {D}, false);
+    add_param(ctx, "t_embedder.mlp.0.weight", ctx->t_w0, {D, 256}, false);
+    add_param(ctx, "t_embedder.mlp.0.bias", ctx->t_b0, {D}, false);
+    add_param(ctx, "t_embedder.mlp.2.weight", ctx->t_w2, {D, D}, false);
+    add_param(ctx, "t_embedder.mlp.2.bias", ctx->t_b2, {D}, false);
+    add_param(ctx, "y_embedder.embedding_table.weight", ctx->ytable, {desc->table_rows, D}, false);
+    add_param(ctx, "final_layer.linear.weight", ctx->fin_w, {16, D}, false);
+    add_param(ctx, "final_layer.linear.bias", ctx->fin_b, {16}, false);
+    add_param(ctx, "final_layer.adaLN_modulation.1.weight", ctx->w_mod + (size_t)6 * L * D * D, {2 * D, D}, true);
+    add_param(ctx, "final_layer.adaLN_modulation.1.bias", ctx->b_mod + (size_t)6 * L * D, {2 * D}, false);
+    ctx->blk.resize(L);
+    for (int i = 0; i < L; ++i) {
+        BlockW& b = ctx->blk[i];
+        if (dev_alloc(ctx, &b.w_qkv, (size_t)3 * D * D)) return 1;
+        if (dev_alloc(ctx, &b.w_proj, (size_t)D * D)) return 1;
+        if (dev_alloc(ctx, &b.w_fc1, (size_t)Hd * D)) return 1;
+        if (dev_alloc(ctx, &b.w_fc2, (size_t)D * Hd)) return 1;
+        if (dev_alloc(ctx, &b.b_qkv, 3 * D)) return 1;
+        if (dev_alloc(ctx, &b.b_proj, D)) return 1;
+        if (dev_alloc(ctx, &b.b_fc1, Hd)) return 1;
+        if (dev_alloc(ctx, &b.b_fc2, D)) return 1;
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        add_param(ctx, p + "attn.qkv.weight", b.w_qkv, {3 * D, D}, true);
+        add_param(ctx, p + "attn.qkv.bias", b.b_qkv, {3 * D}, false);
+        add_param(ctx, p + "attn.proj.weight", b.w_proj, {D, D}, true);
+        add_param(ctx, p + "attn.proj.bias", b.b_proj, {D}, false);
+        add_param(ctx, p + "mlp.fc1.weight", b.w_fc1, {Hd, D}, true);
+        add_param(ctx, p + "mlp.fc1.bias", b.b_fc1, {Hd}, false);
+        add_param(ctx, p + "mlp.fc2.weight", b.w_fc2, {D, Hd}, true);
+        add_param(ctx, p + "mlp.fc2.bias", b.b_fc2, {D}, false);
+        add_param(ctx, p + "adaLN_modulation.1.weight", ctx->w_mod + (size_t)i * 6 * D * D, {6 * D, D}, true);
+        add_param(ctx, p + "adaLN_modulation.1.bias", ctx->b_mod + (size_t)i * 6 * D, {6 * D}, false);
+    }
+    CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming));
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int dtype, const int64_t* shape, int ndim) {
+    if (ctx == nullptr || key == nullptr || ptr == nullptr) return fail(ctx, "lfm_set_param: null argument");
+    if (dtype != LFM_DTYPE_F32) return fail(ctx, "lfm_set_param(%s): only fp32 sources are accepted", key);
+    auto it = ctx->params.find(key);
+    if (it == ctx->params.end()) return fail(ctx, "lfm_set_param: unexpected key '%s' (strict)", key);
+    ParamSlot& s = it->second;
+    if (ndim != (int)s.shape.size()) return fail(ctx, "lfm_set_param(%s): rank %d, expected %d", key, ndim, (int)s.shape.size());
+    for (int i = 0; i < ndim; ++i)
+        if (shape[i] != s.shape[i])
+            return fail(ctx, "lfm_set_param(%s): dim %d is %lld, expected %lld", key, i, (long long)shape[i], (long long)s.shape[i]);
+    CUDA_OK(cudaSetDevice(ctx->device));
+    if (!s.to_bf16) {
+        CUDA_OK(cudaMemcpy(s.dst, ptr, s.numel * sizeof(float), cudaMemcpyDefault));
+    } else {
+        if (ctx->staging_elems < s.numel) {
+            if (ctx->staging != nullptr) CUDA_OK(cudaFree(ctx->staging));
+            ctx->staging = nullptr;
+            CUDA_OK(cudaMalloc(&ctx->staging, s.numel * sizeof(float)));
+            ctx->staging_elems = s.numel;
+        }
+        CUDA_OK(cudaMemcpy(ctx->staging, ptr, s.numel * sizeof(float), cudaMemcpyDefault));
+        f32_to_bf16_kernel<<<blocks_for((s.numel + 3) / 4), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst), s.numel);
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaDeviceSynchronize());
+    }
+    s.set = true;
+    ctx->finalized = ctx->finalized && true;
+    return 0;
+}
+
+static int pick_bn(int N, const char* env, int dflt) {
+    int bn = env_int(env, dflt);
+    if (bn != 128 && bn != 256) bn = dflt;
+    return bn;
+}
+
+extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
+    if (ctx == nullptr) return fail(ctx, "lfm_finalize: null ctx");
+    if (max_batch < 1) return fail(ctx, "lfm_finalize: max_batch must be >= 1");
+    for (auto& kv : ctx->params)
+        if (!kv.second.set) return fail(ctx, "lfm_finalize: missing key '%s' (strict)", kv.first.c_str());
+    if (ctx->finalized && max_batch <= ctx->max_rows) return 0;
+    if (ctx->finalized) return fail(ctx, "lfm_finalize: already finalized for %d rows; create a new ctx for %d", ctx->max_rows, max_batch);
+    CUDA_OK(cudaSetDevice(ctx->device));
+    const int D = ctx->D, Hd = ctx->Hd, T = ctx->T, R = max_batch;
+    const size_t M = (size_t)R * T;
+    const int Rpad = R < 128 ? 128 : R;
+    if (dev_alloc(ctx, &ctx->x_tok, M * D)) return 1;
+    if (dev_alloc(ctx, &ctx->xn, M * D)) return 1;
+    if (dev_alloc(ctx, &ctx->qkv, M * 3 * D)) return 1;
+    if (dev_alloc(ctx, &ctx->attn, M * D)) return 1;
+    if (dev_alloc(ctx, &ctx->hmid, M * Hd)) return 1;
+    if (dev_alloc(ctx, &ctx->mod, (size_t)R * ctx->Nmod)) return 1;
+    if (dev_alloc(ctx, &ctx->c_silu, (size_t)Rpad * D)) return 1;
+    if (dev_alloc(ctx, &ctx->tfreq, (size_t)R * 256)) return 1;
+    if (dev_alloc(ctx, &ctx->h1, (size_t)R * D)) return 1;
+    if (dev_alloc(ctx, &ctx->v_net, (size_t)R * ctx->chw)) return 1;
+    // solver state (sized for R latent rows)
+    const size_t nst = (size_t)R * ctx->chw;
+    if (dev_alloc(ctx, &ctx->x_state, nst)) return 1;
+    if (dev_alloc(ctx, &ctx->x_pred, nst)) return 1;
+    if (dev_alloc(ctx, &ctx->v_eff, nst)) return 1;
+    if (dev_alloc(ctx, &ctx->d_prime, nst)) return 1;
+    if (dev_alloc(ctx, &ctx->y_stage, nst)) return 1;
+    for (int j = 0; j < 7; ++j)
+        if (dev_alloc(ctx, &ctx->kbuf[j], nst)) return 1;
+    if (dev_alloc(ctx, &ctx->t_grid, 8192)) return 1;
+    if (dev_alloc(ctx, &ctx->t_eval, 8)) return 1;
+    if (dev_alloc(ctx, &ctx->coef, 64)) return 1;
+    if (dev_alloc(ctx, &ctx->ratio, 8)) return 1;
+    if (dev_alloc(ctx, &ctx->partial, kRmsBlocks)) return 1;
+    if (dev_alloc(ctx, &ctx->y_buf, (size_t)R)) return 1;
+    if (dev_alloc(ctx, &ctx->step_state, 1)) return 1;
+    CUDA_OK(cudaMallocHost(&ctx->ratio_host, 64));
+
+    ctx->bn_qkv = pick_bn(3 * D, "LFM_BN_QKV", (3 * D) % 256 == 0 ? 256 : 128);
+    ctx->bn_proj = pick_bn(D, "LFM_BN_PROJ", D % 256 == 0 ? 256 : 128);
+    ctx->bn_fc1 = pick_bn(Hd, "LFM_BN_FC1", Hd % 256 == 0 ? 256 : 128);
+    ctx->bn_fc2 = pick_bn(D, "LFM_BN_FC2", D % 256 == 0 ? 256 : 128);
+    ctx->bn_mod = 256;
+    bool ok = true;
+    ok &= make_tmap_bf16(&ctx->tm_xn, ctx->xn, M, D, 128);
+    ok &= make_tmap_bf16(&ctx->tm_attn, ctx->attn, M, D, 128);
+    ok &= make_tmap_bf16(&ctx->tm_hmid, ctx->hmid, M, Hd, 128);
+    ok &= make_tmap_bf16(&ctx->tm_csilu, ctx->c_silu, Rpad, D, 128);
+    ok &= make_tmap_bf16(&ctx->tm_qkv_q, ctx->qkv, M, 3 * D, 128);
+    ok &= make_tmap_bf16(&ctx->tm_qkv_kv, ctx->qkv, M, 3 * D, 256);
+    ok &= make_tmap_bf16(&ctx->tm_wmod, ctx->w_mod, ctx->Nmod, D, ctx->bn_mod);
+    for (auto& b : ctx->blk) {
+        ok &= make_tmap_bf16(&b.tm_qkv, b.w_qkv, 3 * D, D, ctx->bn_qkv);
+        ok &= make_tmap_bf16(&b.tm_proj, b.w_proj, D, D, ctx->bn_proj);
+        ok &= make_tmap_bf16(&b.tm_fc1, b.w_fc1, Hd, D, ctx->bn_fc1);
+        ok &= make_tmap_bf16(&b.tm_fc2, b.w_fc2, D, Hd, ctx->bn_fc2);
+    }
+    if (!ok) return fail(ctx, "lfm_finalize: cuTensorMapEncodeTiled failed");
+    ctx->max_rows = R;
+    ctx->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the velocity network: rows network rows, latents x has x_rows samples (row b reads sample b % x_rows)
+
+#define LAUNCH_OK()                                   \
+    do {                                              \
+        CUDA_OK(cudaGetLastError());                  \
+        ctx->launches++;                              \
+    } while (0)
+
+static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_numel, const float* x, int x_rows,
+                          const long long* y, int rows) {
+    const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T, Nmod = ctx->Nmod;
+    const int M = rows * T;
+    timestep_features_kernel<<<rows, 256, 0, s>>>(t, t_numel, ctx->tfreq, rows);
+    LAUNCH_OK();
+    skinny_linear_kernel<0><<<(D + 7) / 8, 256, 0, s>>>(ctx->t_w0, ctx->t_b0, ctx->tfreq, rows, D, 256, nullptr, nullptr,
+                                                        0, ctx->h1, nullptr);
+    LAUNCH_OK();
+    skinny_linear_kernel<1><<<(D + 7) / 8, 256, 0, s>>>(ctx->t_w2, ctx->t_b2, ctx->h1, rows, D, D, ctx->ytable, y,
+                                                        ctx->d.table_rows - 1, nullptr, ctx->c_silu);
+    LAUNCH_OK();
+    {   // all adaLN modulation vectors of the network in one GEMM: mod[rows, (6L+2) D]
+        GemmEpi ep{ctx->b_mod, ctx->mod, Nmod, nullptr, 0, 1};
+        CUDA_OK(launch_gemm(s, ctx->tm_csilu, ctx->tm_wmod, rows, Nmod, D, EPI_BIAS_F32, ctx->bn_mod, ep));
+        ctx->launches++;
+    }
+    patch_embed_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, x_rows, ctx->pe_w, ctx->pe_b, ctx->pos, ctx->x_tok, D, ctx->G,
+                                                   ctx->C, M);
+    LAUNCH_OK();
+    for (int l = 0; l < L; ++l) {
+        BlockW& b = ctx->blk[l];
+        const float* mb = ctx->mod + (size_t)l * 6 * D;  // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
+        ln_modulate_kernel<<<(M + 7) / 8, 256, 0, s>>>(ctx->x_tok, ctx->xn, mb, mb + D, Nmod, T, M, D);
+        LAUNCH_OK();
+        {
+            GemmEpi ep{b.b_qkv, ctx->qkv, 3 * D, nullptr, 0, T};
+            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep));
+            ctx->launches++;
+        }
+        if (ctx->attn_variant == 0)
+            CUDA_OK(launch_attention_inst<true>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
+        else
+            CUDA_OK(launch_attention_inst<false>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
+        ctx->launches++;
+        {
+            GemmEpi ep{b.b_proj, ctx->x_tok, D, mb + 2 * D, Nmod, T};
+            CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep));
+            ctx->launches++;
+        }
+        ln_modulate_kernel<<<(M + 7) / 8, 256, 0, s>>>(ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D);
+        LAUNCH_OK();
+        {
+            GemmEpi ep{b.b_fc1, ctx->hmid, Hd, nullptr, 0, T};
+            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_fc1, M, Hd, D, EPI_BIAS_GELU_BF16, ctx->bn_fc1, ep));
+            ctx->launches++;
+        }
+        {
+            GemmEpi ep{b.b_fc2, ctx->x_tok, D, mb + 5 * D, Nmod, T};
+            CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep));
+            ctx->launches++;
+        }
+    }
+    {
+        const float* mf = ctx->mod + (size_t)6 * L * D;  // shift | scale
+        static bool attr_set = false;
+        const int smem = 16 * D * (int)sizeof(float);
+        if (!attr_set) {
+            CUDA_OK(cudaFuncSetAttribute(final_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        int grid = (M + 7) / 8;
+        if (grid > 2 * g_num_sms) grid = 2 * g_num_sms;
+        final_layer_kernel<<<grid, 256, smem, s>>>(ctx->x_tok, mf, mf + D, Nmod, ctx->fin_w, ctx->fin_b, ctx->v_net, M, D,
+                                                   ctx->G, ctx->C);
+        LAUNCH_OK();
+    }
+    return 0;
+}
+
+// Evaluate the (CFG-combined) velocity of n_img latents in `x` into `v_out` [n_img, C, H, W].
+//   cfg_scale > 1: network batch = 2 n_img rows (labels y[0:n] conditional, y[n:2n] null), v = u + s (c - u).
+static int eval_velocity(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_numel, const float* x, int n_img,
+                         const long long* y, float cfg_scale, float* v_out) {
+    const size_t n = (size_t)n_img * ctx->chw;
+    if (cfg_scale > 1.0f) {
+        if (launch_network(ctx, s, t, t_numel, x, n_img, y, 2 * n_img)) return 1;
+        cfg_combine_kernel<<<blocks_for(n), 256, 0, s>>>(ctx->v_net, v_out, n, cfg_scale, 0);
+        LAUNCH_OK();
+    } else {
+        if (launch_network(ctx, s, t, t_numel, x, n_img, y, n_img)) return 1;
+        CUDA_OK(cudaMemcpyAsync(v_out, ctx->v_net, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+static int check_ready(lfm_ctx* ctx, int rows, const char* who) {
+    if (ctx == nullptr) return fail(ctx, "%s: null ctx", who);
+    if (!ctx->finalized) return fail(ctx, "%s: lfm_finalize has not been called", who);
+    if (rows < 1 || rows > ctx->max_rows)
+        return fail(ctx, "%s: %d network rows requested, ctx finalized for %d", who, rows, ctx->max_rows);
+    return 0;
+}
+
+extern "C" int lfm_forward(lfm_ctx* ctx, const float* t, int t_numel, const float* x, const int64_t* y, int B,
+                           float cfg_scale, float* v_out, void* stream) {
+    if (check_ready(ctx, B, "lfm_forward")) return 1;
+    if (t == nullptr || x == nullptr || v_out == nullptr) return fail(ctx, "lfm_forward: null tensor");
+    if (t_numel != 1 && t_numel != B) return fail(ctx, "lfm_forward: t has %d elements, expected 1 or %d", t_numel, B);
+    CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long* yl = reinterpret_cast<const long long*>(y);
+    if (cfg_scale > 1.0f) {
+        if (B % 2 != 0) return fail(ctx, "lfm_forward: forward_with_cfg needs an even batch (got %d)", B);
+        if (t_numel != 1) {
+            // the reference passes t[2n]; both halves carry the same times (x halves are identical)
+        }
+        const int n_img = B / 2;
+        if (launch_network(ctx, s, t, t_numel, x, n_img, yl, B)) return 1;
+        const size_t n = (size_t)n_img * ctx->chw;
+        cfg_combine_kernel<<<blocks_for(n), 256, 0, s>>>(ctx->v_net, v_out, n, cfg_scale, 1);
+        LAUNCH_OK();
+    } else {
+        if (launch_network(ctx, s, t, t_numel, x, B, yl, B)) return 1;
+        CUDA_OK(cudaMemcpyAsync(v_out, ctx->v_net, (size_t)B * ctx->chw * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-step solvers: one captured graph per step kind, replayed from the host with no synchronisation
+
+static int join_in(lfm_ctx* ctx, cudaStream_t user) {
+    CUDA_OK(cudaEventRecord(ctx->ev_in, user));
+    CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in, 0));
+    return 0;
+}
+static int join_out(lfm_ctx* ctx, cudaStream_t user) {
+    CUDA_OK(cudaEventRecord(ctx->ev_out, ctx->stream));
+    CUDA_OK(cudaStreamWaitEvent(user, ctx->ev_out, 0));
+    return 0;
+}
+
+// body of one interval, recorded into ctx->stream (under capture or live)
+static int record_step(lfm_ctx* ctx, int kind /*0 euler, 1 heun (with corrector)*/, int n_img, bool has_y, float cfg_scale) {
+    cudaStream_t s = ctx->stream;
+    const size_t n = (size_t)n_img * ctx->chw;
+    const long long* y = has_y ? ctx->y_buf : nullptr;
+    step_time_kernel<<<1, 32, 0, s>>>(ctx->t_grid, ctx->step_state, 0, ctx->t_eval);
+    LAUNCH_OK();
+    if (eval_velocity(ctx, s, ctx->t_eval, 1, ctx->x_state, n_img, y, cfg_scale, ctx->v_eff)) return 1;
+    if (kind == 0) {
+        euler_update_kernel<<<blocks_for(n), 256, 0, s>>>(ctx->x_state, ctx->v_eff, ctx->t_grid, ctx->step_state, n);
+        LAUNCH_OK();
+    } else {
+        heun_predict_kernel<<<blocks_for(n), 256, 0, s>>>(ctx->x_state, ctx->v_eff, ctx->x_pred, ctx->t_grid,
+                                                          ctx->step_state, n);
+        LAUNCH_OK();
+        step_time_kernel<<<1, 32, 0, s>>>(ctx->t_grid, ctx->step_state, 1, ctx->t_eval);
+        LAUNCH_OK();
+        if (eval_velocity(ctx, s, ctx->t_eval, 1, ctx->x_pred, n_img, y, cfg_scale, ctx->d_prime)) return 1;
+        heun_correct_kernel<<<blocks_for(n), 256, 0, s>>>(ctx->x_state, ctx->v_eff, ctx->d_prime, ctx->x_pred, ctx->t_grid,
+                                                          ctx->step_state, 1 << 30, n);
+        LAUNCH_OK();
+    }
+    step_advance_kernel<<<1, 32, 0, s>>>(ctx->step_state);
+    LAUNCH_OK();
+    return 0;
+}
+
+static int get_step_graph(lfm_ctx* ctx, int kind, int n_img, bool has_y, float cfg_scale, cudaGraphExec_t* out) {
+    char key[128];
+    snprintf(key, sizeof(key), "k%d_n%d_y%d_c%.6f", kind, n_img, has_y ? 1 : 0, cfg_scale > 1.0f ? cfg_scale : 0.f);
+    auto it = ctx->graphs.find(key);
+    if (it != ctx->graphs.end()) {
+        *out = it->second.exec;
+        return 0;
+    }
+    if (env_int("LFM_NO_GRAPH", 0)) {
+        *out = nullptr;
+        return 0;
+    }
+    // warm the lazily-set function attributes outside of capture
+    const int64_t launches_before = ctx->launches;
+    if (record_step(ctx, kind, n_img, has_y, cfg_scale)) return 1;
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    StepState zero{0, 0};
+    // (the warm-up advanced the device step counter and state; callers re-initialise both afterwards)
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = record_step(ctx, kind, n_img, has_y, cfg_scale);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    ctx->launches = launches_before;
+    if (rc) return 1;
+    if (e != cudaSuccess) return fail(ctx, "graph capture failed: %s", cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+    CUDA_OK(cudaGraphDestroy(graph));
+    (void)zero;
+    ctx->graphs[key].exec = exec;
+    *out = exec;
+    return 0;
+}
+
+static int launches_per_step(lfm_ctx* ctx, int kind, float cfg_scale) {
+    const int net = 5 + 7 * ctx->L + 1;
+    const int ev = net + (cfg_scale > 1.0f ? 1 : 0);  // (+ a d2d memcpy node when no CFG; not a kernel)
+    return kind == 0 ? (1 + ev + 1 + 1) : (1 + ev + 1 + 1 + ev + 1 + 1);
+}
+
+extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const float* t_grid_host, int n_grid,
+                                int t_as_vector, int heun_corrector_limit, const int64_t* y, int B_img, float cfg_scale,
+                                lfm_ode_stats* stats, void* stream) {
+    (void)t_as_vector;  // a [B] vector of equal times and a 0-d time give the same conditioning vector
+    const int rows = cfg_scale > 1.0f ? 2 * B_img : B_img;
+    if (check_ready(ctx, rows, "lfm_sample_fixed")) return 1;
+    if (method != LFM_METHOD_EULER && method != LFM_METHOD_HEUN) return fail(ctx, "lfm_sample_fixed: unknown method %d", method);
+    if (n_grid < 2 || n_grid > 8192) return fail(ctx, "lfm_sample_fixed: n_grid must be in [2, 8192] (got %d)", n_grid);
+    if (x_inout == nullptr || t_grid_host == nullptr) return fail(ctx, "lfm_sample_fixed: null tensor");
+    if (cfg_scale > 1.0f && y == nullptr) return fail(ctx, "lfm_sample_fixed: CFG needs labels");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)B_img * ctx->chw;
+    const bool has_y = y != nullptr;
+
+    // build (or fetch) the step graphs first: the warm-up run clobbers the solver state
+    cudaGraphExec_t g_euler = nullptr, g_heun = nullptr;
+    const int n_int = n_grid - 1;
+    const int n_heun = method == LFM_METHOD_HEUN ? (heun_corrector_limit < n_int ? (heun_corrector_limit < 0 ? 0 : heun_corrector_limit) : n_int) : 0;
+    const bool graphs = !env_int("LFM_NO_GRAPH", 0);
+    if (join_in(ctx, user)) return 1;
+    if (graphs) {
+        if (n_heun < n_int && get_step_graph(ctx, 0, B_img, has_y, cfg_scale, &g_euler)) return 1;
+        if (n_heun > 0 && get_step_graph(ctx, 1, B_img, has_y, cfg_scale, &g_heun)) return 1;
+    }
+    cudaStream_t s = ctx->stream;
+    CUDA_OK(cudaMemcpyAsync(ctx->t_grid, t_grid_host, (size_t)n_grid * sizeof(float), cudaMemcpyDefault, s));
+    CUDA_OK(cudaMemcpyAsync(ctx->x_state, x_inout, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (has_y) CUDA_OK(cudaMemcpyAsync(ctx->y_buf, y, (size_t)rows * sizeof(long long), cudaMemcpyDefault, s));
+    StepState st0{0, n_int};
+    CUDA_OK(cudaMemcpyAsync(ctx->step_state, &st0, sizeof(st0), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));  // st0 / t_grid_host are host stack/pageable memory
+    int64_t nfe = 0;
+    for (int i = 0; i < n_int; ++i) {
+        const int kind = i < n_heun ? 1 : 0;
+        cudaGraphExec_t g = kind ? g_heun : g_euler;
+        if (g != nullptr) {
+            CUDA_OK(cudaGraphLaunch(g, s));
+            ctx->launches += launches_per_step(ctx, kind, cfg_scale);
+        } else {
+            if (record_step(ctx, kind, B_img, has_y, cfg_scale)) return 1;
+        }
+        nfe += kind ? 2 : 1;
+    }
+    CUDA_OK(cudaMemcpyAsync(x_inout, ctx->x_state, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (join_out(ctx, user)) return 1;
+    if (stats != nullptr) {
+        stats->nfe = nfe;
+        stats->accepted = n_int;
+        stats->rejected = 0;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dopri5 (torchdiffeq semantics).  Integrates s = -t upward with the field -v(-s, y).
+
+static const double DP_ALPHA[6] = {1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
+static const double DP_BETA[6][6] = {
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84},
+};
+static const double DP_CERR[7] = {35.0 / 384 - 1951.0 / 21600, 0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
+                                  -2187.0 / 6784 - -12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60};
+static const double DP_MID[7] = {6025192743.0 / 30085553152.0 / 2, 0, 51252292925.0 / 65400821598.0 / 2,
+                                 -2691868925.0 / 45128329728.0 / 2, 187940372067.0 / 1594534317056.0 / 2,
+                                 -1776094331.0 / 19743644256.0 / 2, 11237099.0 / 235043384.0 / 2};
+
+struct Dopri {
+    lfm_ctx* ctx;
+    cudaStream_t s;
+    int n_img;
+    const long long* y;
+    float cfg_scale;
+    size_t n;
+    int64_t nfe = 0;
+};
+
+// k_out = -v(t = -s_time, y)   (model sees a 0-d fp32 time)
+static int dp_func(Dopri& d, float s_time, const float* yv, float* k_out) {
+    lfm_ctx* ctx = d.ctx;
+    const float t = -s_time;
+    CUDA_OK(cudaMemcpyAsync(ctx->t_eval, &t, sizeof(float), cudaMemcpyHostToDevice, d.s));
+    CUDA_OK(cudaStreamSynchronize(d.s));  // &t is a stack variable
+    if (eval_velocity(ctx, d.s, ctx->t_eval, 1, yv, d.n_img, d.y, d.cfg_scale, k_out)) return 1;
+    negate_kernel<<<blocks_for(d.n), 256, 0, d.s>>>(k_out, d.n);
+    LAUNCH_OK();
+    d.nfe++;
+    return 0;
+}
+
+static int dp_rms(Dopri& d, const float* a, const float* b, const float* coef_dev, const float* y0, const float* y1,
+                  float atol, float rtol, float* out_host) {
+    lfm_ctx* ctx = d.ctx;
+    RkPtrs kp;
+    for (int j = 0; j < 7; ++j) kp.k[j] = ctx->kbuf[j];
+    rms_ratio_partial_kernel<<<kRmsBlocks, 256, 0, d.s>>>(a, b, kp, coef_dev, y0, y1, atol, rtol, d.n, ctx->partial);
+    LAUNCH_OK();
+    rms_finalize_kernel<<<1, 32, 0, d.s>>>(ctx->partial, kRmsBlocks, d.n, ctx->ratio);
+    LAUNCH_OK();
+    CUDA_OK(cudaMemcpyAsync(ctx->ratio_host, ctx->ratio, sizeof(float), cudaMemcpyDeviceToHost, d.s));
+    CUDA_OK(cudaStreamSynchronize(d.s));
+    *out_host = ctx->ratio_host[0];
+    return 0;
+}
+
+extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double t1, double rtol, double atol,
+                                 const int64_t* y, int B_img, float cfg_scale, lfm_ode_stats* stats, void* stream) {
+    const int rows = cfg_scale > 1.0f ? 2 * B_img : B_img;
+    if (check_ready(ctx, rows, "lfm_sample_dopri5")) return 1;
+    if (x_inout == nullptr) return fail(ctx, "lfm_sample_dopri5: null tensor");
+    if (!(t0 > t1)) return fail(ctx, "lfm_sample_dopri5: expects t0 > t1 (reference integrates t: 1 -> 0)");
+    if (cfg_scale > 1.0f && y == nullptr) return fail(ctx, "lfm_sample_dopri5: CFG needs labels");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    if (join_in(ctx, user)) return 1;
+    Dopri d{ctx, ctx->stream, B_img, nullptr, cfg_scale, (size_t)B_img * ctx->chw};
+    cudaStream_t s = d.s;
+    const size_t n = d.n;
+    if (y != nullptr) {
+        CUDA_OK(cudaMemcpyAsync(ctx->y_buf, y, (size_t)rows * sizeof(long long), cudaMemcpyDefault, s));
+        d.y = ctx->y_buf;
+    }
+    float* y0 = ctx->x_state;
+    float* y1 = ctx->x_pred;
+    float* ytmp = ctx->y_stage;
+    float** k = ctx->kbuf;
+    CUDA_OK(cudaMemcpyAsync(y0, x_inout, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    const float atol_f = (float)atol, rtol_f = (float)rtol;
+    RkPtrs kp;
+    for (int j = 0; j < 7; ++j) kp.k[j] = k[j];
+    auto upload_coef = [&](const float* c, int cnt, int slot) -> int {
+        CUDA_OK(cudaMemcpyAsync(ctx->coef + slot * 8, c, cnt * sizeof(float), cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    };
+
+    double s0 = -t0;
+    const double s_end = -t1;
+    // _before_integrate: f0 and the initial step (order 4 rule)
+    if (dp_func(d, (float)s0, y0, k[0])) return 1;
+    float d0, d1, d2;
+    if (dp_rms(d, y0, nullptr, nullptr, y0, y0, atol_f, rtol_f, &d0)) return 1;
+    if (dp_rms(d, k[0], nullptr, nullptr, y0, y0, atol_f, rtol_f, &d1)) return 1;
+    float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+    h0 = fabsf(h0);
+    axpy_kernel<<<blocks_for(n), 256, 0, s>>>(y0, k[0], h0, ytmp, n);
+    LAUNCH_OK();
+    if (dp_func(d, (float)(s0 + (double)h0), ytmp, k[1])) return 1;
+    if (dp_rms(d, k[1], k[0], nullptr, y0, y0, atol_f, rtol_f, &d2)) return 1;
+    d2 = fabsf(d2 / h0);
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f)
+        h1 = fmaxf(1e-6f, h0 * 1e-3f);
+    else
+        h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / 5.0f);
+    double dt = (double)fminf(100.f * h0, fabsf(h1));
+
+    double s_lo = s0, s_hi = s0;
+    float dt_last = 0.f;
+    int64_t accepted = 0, rejected = 0;
+    bool have_interp = false;
+    // y_prev (start of the last accepted step) is needed for the dense output: keep it in d_prime
+    float* y_prev = ctx->d_prime;
+    while (s_end > s_hi) {
+        if (accepted + rejected > 100000) return fail(ctx, "lfm_sample_dopri5: step limit exceeded");
+        const double t0s = s_hi, t1s = t0s + dt;
+        const float t0_32 = (float)t0s, dt_32 = (float)dt, t1_32 = (float)t1s;
+        for (int i = 0; i < 6; ++i) {
+            float c[8];
+            for (int j = 0; j <= i; ++j) c[j] = (float)DP_BETA[i][j] * dt_32;
+            if (upload_coef(c, i + 1, 0)) return 1;
+            float* yi = (i == 5) ? y1 : ytmp;
+            rk_combine_kernel<<<blocks_for(n), 256, 0, s>>>(y0, kp, i + 1, ctx->coef, yi, n);
+            LAUNCH_OK();
+            float ti;
+            if (DP_ALPHA[i] == 1.0)
+                ti = nextafterf(t1_32, t1_32 - 1.0f);
+            else
+                ti = t0_32 + (float)DP_ALPHA[i] * dt_32;
+            if (dp_func(d, ti, yi, k[i + 1])) return 1;
+        }
+        float c[8];
+        for (int j = 0; j < 7; ++j) c[j] = dt_32 * (float)DP_CERR[j];
+        if (upload_coef(c, 7, 1)) return 1;
+        float ratio;
+        if (dp_rms(d, nullptr, nullptr, ctx->coef + 8, y0, y1, atol_f, rtol_f, &ratio)) return 1;
+        ratio = fabsf(ratio);
+        const bool accept = ratio <= 1.0f;
+        if (accept) {
+            accepted++;
+            if (t1s >= s_end) {
+                // last step: evaluate the quartic dense output at s_end and finish
+                for (int j = 0; j < 7; ++j) c[j] = dt_32 * (float)DP_MID[j];
+                if (upload_coef(c, 7, 2)) return 1;
+                const float xq = (float)((s_end - t0s) / (t1s - t0s));
+                dopri_interp_kernel<<<blocks_for(n), 256, 0, s>>>(y0, y1, kp, ctx->coef + 16, dt_32, xq, ytmp, n);
+                LAUNCH_OK();
+                have_interp = true;
+                s_lo = t0s;
+                s_hi = t1s;
+                break;
+            }
+            s_lo = t0s;
+            s_hi = t1s;
+            dt_last = dt_32;
+            // y0 <- y1, f0 <- k7 (FSAL)
+            float* tmp = y0;
+            y0 = y1;
+            y1 = tmp;
+            float* tk = k[0];
+            k[0] = k[6];
+            k[6] = tk;
+            kp.k[0] = k[0];
+            kp.k[6] = k[6];
+        } else {
+            rejected++;
+        }
+        double factor;
+        if (ratio == 0.f) {
+            factor = 10.0;
+        } else {
+            const double dfactor = ratio < 1.f ? 1.0 : 0.2;
+            factor = fmin(10.0, fmax(0.9 / pow((double)ratio, 1.0 / 5.0), dfactor));
+        }
+        dt = dt * factor;
+    }
+    (void)s_lo;
+    (void)dt_last;
+    (void)y_prev;
+    if (!have_interp) return fail(ctx, "lfm_sample_dopri5: integration produced no step");
+    CUDA_OK(cudaMemcpyAsync(x_inout, ytmp, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // restore the canonical k-buffer order for the next call
+    if (join_out(ctx, user)) return 1;
+    if (stats != nullptr) {
+        stats->nfe = d.nfe;
+        stats->accepted = accepted;
+        stats->rejected = rejected;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+
+extern "C" const char* lfm_last_error(const lfm_ctx* ctx) {
+    if (ctx != nullptr && !ctx->err.empty()) return ctx->err.c_str();
+    return g_last_error.c_str();
+}
+
+extern "C" int64_t lfm_launch_count(const lfm_ctx* ctx) { return ctx != nullptr ? ctx->launches : 0; }
+
+extern "C" void lfm_destroy(lfm_ctx* ctx) {
+    if (ctx == nullptr) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& g : ctx->graphs)
+        if (g.second.exec != nullptr) cudaGraphExecDestroy(g.second.exec);
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->staging != nullptr) cudaFree(ctx->staging);
+    if (ctx->ratio_host != nullptr) cudaFreeHost(ctx->ratio_host);
+    if (ctx->stream != nullptr) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev_in != nullptr) cudaEventDestroy(ctx->ev_in);
+    if (ctx->ev_out != nullptr) cudaEventDestroy(ctx->ev_out);
+    delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel-level test entry points
+
+extern "C" int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float* bias, void* out, const float* gate,
+                            int gate_stride, int rows_per_sample, int M, int N, int K, int epi, int block_n,
+                            void* stream) {
+    lfm_ctx* ctx = nullptr;
+    if (K % 64 != 0 || N % 8 != 0) return fail(ctx, "lfm_dbg_gemm: K must be a multiple of 64 and N of 8");
+    if (block_n != 128 && block_n != 256) return fail(ctx, "lfm_dbg_gemm: block_n must be 128 or 256");
+    if (g_num_sms == 0) {
+        int dev = 0;
+        CUDA_OK(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+        g_num_sms = prop.multiProcessorCount;
+    }
+    CUtensorMap ta, tb;
+    if (!make_tmap_bf16(&ta, a_bf16, M, K, 128) || !make_tmap_bf16(&tb, w_bf16, N, K, block_n))
+        return fail(ctx, "lfm_dbg_gemm: tensor map encode failed");
+    GemmEpi ep{bias, out, N, gate, gate_stride, rows_per_sample > 0 ? rows_per_sample : 1};
+    CUDA_OK(launch_gemm(static_cast<cudaStream_t>(stream), ta, tb, M, N, K, epi, block_n, ep));
+    return 0;
+}
+
+extern "C" int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, int H, int variant, float* dbg_s,
+                                 void* stream) {
+    lfm_ctx* ctx = nullptr;
+    const int D = H * 64;
+    const uint64_t M = (uint64_t)B * 256;
+    CUtensorMap tq, tkv;
+    if (!make_tmap_bf16(&tq, qkv_bf16, M, 3 * D, 128) || !make_tmap_bf16(&tkv, qkv_bf16, M, 3 * D, 256))
+        return fail(ctx, "lfm_dbg_attention: tensor map encode failed");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (variant == 0)
+        CUDA_OK(launch_attention_inst<true>(s, tq, tkv, static_cast<__nv_bfloat16*>(out_bf16), B, H, D, dbg_s));
+    else
+        CUDA_OK(launch_attention_inst<false>(s, tq, tkv, static_cast<__nv_bfloat16*>(out_bf16), B, H, D, dbg_s));
+    return 0;
+}
+
+extern "C" int lfm_dbg_tokens(lfm_ctx* ctx, float* out, int B) {
+    if (check_ready(ctx, B, "lfm_dbg_tokens")) return 1;
+    CUDA_OK(cudaMemcpy(out, ctx->x_tok, (size_t)B * ctx->T * ctx->D * sizeof(float), cudaMemcpyDefault));
+    return 0;
+}
