@@ -376,7 +376,7 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
     if (dev_alloc(ctx, &ctx->y_stage, nst)) return 1;
     for (int j = 0; j < 7; ++j)
         if (dev_alloc(ctx, &ctx->kbuf[j], nst)) return 1;
-    if (dev_alloc(ctx, &ctx->t_grid, 8192)) return 1;
+    if (dev_alloc(ctx, &ctx->t_grid, 8192 + 64)) return 1;
     if (dev_alloc(ctx, &ctx->t_eval, 8)) return 1;
     if (dev_alloc(ctx, &ctx->coef, 64)) return 1;
     if (dev_alloc(ctx, &ctx->ratio, 8)) return 1;
@@ -477,7 +477,8 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         static bool attr_set = false;
         const int smem = 16 * D * (int)sizeof(float);
         if (!attr_set) {
-            CUDA_OK(cudaFuncSetAttribute(final_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            // opt in once for the largest supported width (hidden_size <= 1536)
+            CUDA_OK(cudaFuncSetAttribute(final_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1536 * 4));
             attr_set = true;
         }
         int grid = (M + 7) / 8;

@@ -1,0 +1,301 @@
+"""Parity tests proper (B200 only, `-m gpu`): the CUDA path, called through the C ABI (liblfm_b200.so via
+lfm_b200's ctypes binding), against the CPU oracle, the committed reference fixtures, and size-independent
+properties at BASELINE.json's full sizes.
+
+Tolerances (the reference pins none).  The CUDA path keeps the residual stream, LayerNorm
+statistics, softmax, adaLN parameters, the ODE state and time in fp32 and rounds only tensor-core operands and
+the stored qkv / attention / MLP-hidden activations to bf16:
+  * one network evaluation vs the fp32 reference fixture .......... rel-L2 <= 2e-3   (measured ~1.2e-4)
+  * end-to-end sampler output vs the fp32 reference fixture ....... rel-L2 <= 2e-3   (measured ~3e-5)
+  * solver arithmetic given identical velocities .................. bit-exact / <= 1e-6
+  * kernel-level GEMM vs fp32 matmul of the same bf16 operands .... fp32 out <= 1e-5, bf16 out <= 4e-3 (1 bf16 ulp)
+"""
+import ctypes as C
+import types
+
+import pytest
+import torch
+
+import lfm_b200
+from lfm_b200 import _lib
+from oracle import dit as odit
+from oracle import solvers as osol
+from tests._util import T, cfg_from_golden, load_golden, oracle_model, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_NFE = 2e-3
+TOL_E2E = 2e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def P(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def make_net(cfg, sd, dev, max_batch=None):
+    net = lfm_b200.DiT(img_resolution=cfg.img_resolution, patch_size=cfg.patch_size, in_channels=cfg.in_channels,
+                       hidden_size=cfg.hidden_size, depth=cfg.depth, num_heads=cfg.num_heads,
+                       label_dropout=cfg.label_dropout, num_classes=cfg.num_classes, max_batch=max_batch)
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev).eval()
+
+
+def make_big(model_type, dev, num_classes, label_dropout, max_batch):
+    from lfm_b200.synthetic import synthetic_state_dict
+    with torch.device("meta"):
+        net = lfm_b200.DiT_models[model_type](img_resolution=32, in_channels=4, label_dropout=label_dropout,
+                                              num_classes=num_classes, max_batch=max_batch)
+    sd = synthetic_state_dict(net, 1)
+    net = net.to_empty(device="cpu")
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev).eval()
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+
+
+@pytest.mark.parametrize("M,N,K,epi,bn", [
+    (128, 128, 64, 3, 128), (256, 512, 1024, 0, 256), (512, 1024, 1024, 1, 256), (512, 1024, 4096, 2, 256),
+    (512, 1024, 4096, 2, 128), (64, 2048, 1024, 3, 256), (4, 1024, 256, 3, 256), (256, 1152, 384, 0, 256),
+    (256, 1152, 384, 1, 128), (16384, 3072, 1024, 0, 256), (16384, 1024, 1024, 2, 128)])
+def test_gemm_epilogues(dev, M, N, K, epi, bn):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K + epi)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    Tt = 256
+    gate = torch.randn((M + Tt - 1) // Tt, 3 * N, generator=g).to(dev)
+    acc = a.float() @ w.float().t() + bias
+    if epi == 0:
+        out, ref, tol = torch.zeros(M, N, device=dev, dtype=torch.bfloat16), acc, 4e-3
+    elif epi == 1:
+        out, ref, tol = (torch.zeros(M, N, device=dev, dtype=torch.bfloat16),
+                         torch.nn.functional.gelu(acc, approximate="tanh"), 4e-3)
+    elif epi == 2:
+        x0 = torch.randn(M, N, generator=g).to(dev)
+        out = x0.clone()
+        ref = x0 + gate[torch.arange(M, device=dev) // Tt, N:2 * N] * acc
+        tol = 1e-5
+    else:
+        out, ref, tol = torch.zeros(M, N, device=dev), acc, 1e-5
+    rc = lib.lfm_dbg_gemm(P(a), P(w), P(bias), P(out), C.c_void_p(gate.data_ptr() + N * 4), 3 * N, Tt, M, N, K, epi, bn,
+                          None)
+    torch.cuda.synchronize()
+    assert rc == 0, _lib.last_error()
+    assert rel_l2(out.float().cpu(), ref.cpu()) < tol
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("B,H", [(1, 1), (2, 4), (3, 12), (64, 16)])
+def test_attention(dev, variant, B, H):
+    lib = _lib.load()
+    D = H * 64
+    g = torch.Generator().manual_seed(B * 100 + H)
+    qkv = torch.randn(B * 256, 3 * D, generator=g).to(dev).bfloat16()
+    q, k, v = qkv.float().reshape(B, 256, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax((q @ k.transpose(-1, -2)) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(B * 256, D)
+    out = torch.zeros(B * 256, D, device=dev, dtype=torch.bfloat16)
+    rc = lib.lfm_dbg_attention(P(qkv), P(out), B, H, variant, None, None)
+    torch.cuda.synchronize()
+    assert rc == 0, _lib.last_error()
+    assert rel_l2(out.float().cpu(), ref.cpu()) < 5e-3   # P and O are rounded to bf16
+
+
+# ------------------------------------------------------------------------------------------------ reference fixtures
+
+
+@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"])
+def test_forward_vs_reference_fixture(dev, name):
+    g = load_golden(name)
+    cfg = cfg_from_golden(g)
+    net = make_net(cfg, odit.synthetic_state_dict(cfg, int(g["weight_seed"])), dev)
+    x = T(g["x"]).to(dev)
+    v = net(T(g["t_scalar"]).to(dev), x)                       # 0-d t, y=None
+    assert rel_l2(v.cpu(), g["v_scalar_ynone"]) < TOL_NFE
+    v = net(T(g["t_vec"]).to(dev), x, T(g["y"]).to(dev))       # [B] t, labels
+    assert rel_l2(v.cpu(), g["v_vec_y"]) < TOL_NFE
+    v = net(float(g["t_scalar"]), x)                           # python float t
+    assert rel_l2(v.cpu(), g["v_scalar_ynone"]) < TOL_NFE
+    if cfg.num_classes > 1:
+        x2 = torch.cat([x, x])
+        v = net.forward_with_cfg(torch.full((4,), 0.4, device=dev), x2, T(g["y_cfg"]).to(dev), cfg_scale=1.5)
+        assert rel_l2(v.cpu(), g["v_cfg_1p5"]) < TOL_NFE
+        assert torch.equal(v[:2], v[2:])
+        with pytest.raises(IndexError):
+            net(0.5, x, torch.tensor([0, cfg.num_classes + 5], device=dev))
+
+
+@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"])
+def test_fixed_step_samplers_vs_reference_fixture(dev, name):
+    g = load_golden(name)
+    cfg = cfg_from_golden(g)
+    net = make_net(cfg, odit.synthetic_state_dict(cfg, int(g["weight_seed"])), dev)
+    x = T(g["x"]).to(dev)
+    if cfg.num_classes > 1:
+        xs, mk = torch.cat([x, x]), dict(y=T(g["y_cfg"]).to(dev), cfg_scale=1.5)
+    else:
+        xs, mk = x, {}
+    kw = dict(clip_denoised=False, model_kwargs=mk, sigma_min=1e-5, sigma_max=1.0)
+    out = lfm_b200.karras_sample(net, xs, 6, sampler="euler", **kw)
+    assert rel_l2(out.cpu(), g["euler6"]) < TOL_E2E and net.last_stats["nfe"] == 5
+    out = lfm_b200.karras_sample(net, xs, 5, sampler="heun", **kw)
+    assert rel_l2(out.cpu(), g["heun5"]) < TOL_E2E and net.last_stats["nfe"] == 8
+    args = types.SimpleNamespace(num_steps=6, method="euler")
+    out2 = lfm_b200.sample_from_model_with_fixed_step_solver(net, xs, mk, None, args)
+    assert rel_l2(out2.cpu(), g["euler6"]) < TOL_E2E
+
+
+def test_heun_reference_quirk(dev):
+    g = load_golden("mini_uncond")
+    cfg = cfg_from_golden(g)
+    net = make_net(cfg, odit.synthetic_state_dict(cfg, int(g["weight_seed"])), dev)
+    x = T(g["x"]).to(dev)
+    kw = dict(clip_denoised=False, model_kwargs={}, sigma_min=1e-5, sigma_max=1.0, sampler="heun")
+    out = lfm_b200.karras_sample(net, x, 43, **kw)
+    assert rel_l2(out.cpu(), g["heun43"]) < TOL_E2E
+    assert net.last_stats["nfe"] == 2 * 39 + 3                  # intervals 39..41 are Euler-only
+    out = lfm_b200.karras_sample(net, x, 43, heun_corrector_limit=10 ** 6, **kw)
+    assert net.last_stats["nfe"] == 84
+
+
+def test_full_size_dit_l2_fixture(dev):
+    g = load_golden("dit_l2")
+    net = make_big("DiT-L/2", dev, 1, 0.0, 2)
+    x = T(g["x"]).to(dev)
+    v = net(T(g["t"]).to(dev), x)
+    assert rel_l2(v.cpu(), g["v"]) < TOL_NFE
+    out = lfm_b200.karras_sample(net, x, 3, clip_denoised=False, model_kwargs={}, sigma_min=1e-5, sigma_max=1.0,
+                                 sampler="euler")
+    assert rel_l2(out.cpu(), g["euler3"]) < TOL_E2E
+
+
+def test_full_size_dit_b2_cfg_fixture(dev):
+    g = load_golden("dit_b2")
+    net = make_big("DiT-B/2", dev, 1000, 0.1, 4)
+    x = T(g["x"]).to(dev)
+    v = net.forward_with_cfg(T(g["t"]).to(dev), torch.cat([x, x]), T(g["y_cfg"]).to(dev), cfg_scale=1.5)
+    assert rel_l2(v.cpu(), g["v_cfg_1p5"]) < TOL_NFE
+
+
+# ------------------------------------------------------------------------------------------------ torchdiffeq paths vs oracle
+
+
+def test_torchdiffeq_euler_and_dopri5_vs_oracle(dev):
+    g = load_golden("mini_uncond")
+    cfg = cfg_from_golden(g)
+    sd = odit.synthetic_state_dict(cfg, int(g["weight_seed"]))
+    net = make_net(cfg, sd, dev)
+    x = T(g["x"])
+    f = oracle_model(sd, cfg)
+    args = types.SimpleNamespace(method="euler", step_size=0.1, perturb=False, cfg_scale=1.0, compute_nfe=True)
+    traj, nfe = lfm_b200.sample_from_model(net, x.to(dev), {}, args)
+    ref, n = osol.tdq_euler(f, x, 0.1)
+    assert traj.shape == (2, 2, 4, 32, 32) and int(nfe) == n == 10
+    assert torch.equal(traj[0].cpu(), x)
+    assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
+    args = types.SimpleNamespace(method="dopri5", atol=1e-5, rtol=1e-5, cfg_scale=1.0, compute_nfe=True)
+    traj, nfe = lfm_b200.sample_from_model(net, x.to(dev), {}, args)
+    ref, st = osol.tdq_dopri5(f, x)
+    assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
+    s = net.last_stats
+    assert s["nfe"] == 2 + 6 * (s["accepted"] + s["rejected"]) == int(nfe)
+    # bf16 noise in v perturbs the embedded error estimate at rtol 1e-5: step counts may differ by a step or two
+    assert abs(s["nfe"] - st.nfe) <= 12
+    # at a tolerance well above the bf16 noise floor the accept/reject sequence must agree exactly
+    args = types.SimpleNamespace(method="dopri5", atol=1e-2, rtol=1e-2, cfg_scale=1.0, compute_nfe=True)
+    traj, nfe = lfm_b200.sample_from_model(net, x.to(dev), {}, args)
+    ref, st = osol.tdq_dopri5(f, x, rtol=1e-2, atol=1e-2)
+    assert (net.last_stats["nfe"], net.last_stats["accepted"], net.last_stats["rejected"]) == (st.nfe, st.accepted, st.rejected)
+    assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
+    with pytest.raises(NotImplementedError):
+        lfm_b200.sample_from_model(net, x.to(dev), {}, types.SimpleNamespace(method="rk4", step_size=0.1, cfg_scale=1.0))
+
+
+def test_dopri5_with_cfg_vs_oracle(dev):
+    g = load_golden("mini_cond")
+    cfg = cfg_from_golden(g)
+    sd = odit.synthetic_state_dict(cfg, int(g["weight_seed"]))
+    net = make_net(cfg, sd, dev)
+    x = T(g["x"])
+    y2 = T(g["y_cfg"])
+    args = types.SimpleNamespace(method="dopri5", atol=1e-3, rtol=1e-3, cfg_scale=1.5, compute_nfe=False)
+    traj = lfm_b200.sample_from_model(net, torch.cat([x, x]).to(dev), dict(y=y2.to(dev), cfg_scale=1.5), args)
+    ref, st = osol.tdq_dopri5(oracle_model(sd, cfg, y2, 1.5), torch.cat([x, x]), rtol=1e-3, atol=1e-3)
+    assert traj.shape[1] == 4 and torch.equal(traj[-1][:2], traj[-1][2:])
+    assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
+    assert net.last_stats["nfe"] == st.nfe
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+
+
+@pytest.fixture(scope="module")
+def dit_l2_b64(dev):
+    return make_big("DiT-L/2", dev, 1, 0.0, 64)
+
+
+def test_full_size_properties_dit_l2_b64(dev, dit_l2_b64):
+    """BASELINE.json configs[1] size (DiT-L/2, batch 64): properties that need no full-size oracle run."""
+    net = dit_l2_b64
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(64, 4, 32, 32, generator=g).to(dev)
+    t = torch.tensor(0.6, device=dev)
+    v1 = net(t, x)
+    v2 = net(t, x)
+    assert torch.equal(v1, v2)                                   # deterministic / idempotent
+    assert torch.isfinite(v1).all() and float(v1.abs().mean()) > 1e-3
+    # samples are independent: any sub-batch gives the same rows (same kernels, same per-row arithmetic)
+    v_half = net(t, x[16:48])
+    assert rel_l2(v_half.cpu(), v1[16:48].cpu()) < 1e-6
+    perm = torch.randperm(64, generator=g).to(dev)
+    assert rel_l2(net(t, x[perm]).cpu(), v1[perm].cpu()) < 1e-6
+    # a [B] vector of equal times == a 0-d time (models/DiT.py:65-66 broadcast)
+    assert torch.equal(net(torch.full((64,), 0.6, device=dev), x), v1)
+    # spot-check 2 rows of the batch against the fp32 oracle
+    from lfm_b200.synthetic import synthetic_state_dict
+    cfg = odit.make_config("DiT-L/2", num_classes=1, label_dropout=0.0)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    ref = odit.dit_forward(sd, cfg, torch.tensor(0.6), x[[3, 60]].cpu())
+    assert rel_l2(v1[[3, 60]].cpu(), ref) < TOL_NFE
+    # one Euler interval == x + dt * v   (solver arithmetic is exact fp32)
+    nodes = torch.tensor([0.6, 0.35])
+    args = types.SimpleNamespace(method="euler", step_size=0.02, perturb=False, cfg_scale=1.0, compute_nfe=False)
+    from lfm_b200 import solvers
+    xf, st = solvers._run_fixed(net, x, None, 1.0, nodes, "euler", 0, 0)
+    assert torch.equal(xf, x + v1 * (nodes[1] - nodes[0]).item()) or rel_l2(xf.cpu(), (x + v1 * (nodes[1] - nodes[0]).to(dev)).cpu()) < 1e-7
+    # Euler-50 end to end: finite, moved, and two half-batches reproduce the full batch
+    full = lfm_b200.sample_from_model(net, x, {}, args)[-1]
+    assert net.last_stats["nfe"] == 50 and torch.isfinite(full).all()
+    halves = torch.cat([lfm_b200.sample_from_model(net, x[:32], {}, args)[-1],
+                        lfm_b200.sample_from_model(net, x[32:], {}, args)[-1]])
+    assert rel_l2(halves.cpu(), full.cpu()) < 1e-5
+    assert float((full - x).abs().mean()) > 1e-2
+
+
+def test_cfg_identity_dit_b2_full(dev):
+    """configs[2] shape (DiT-B/2, 32 images x2 under CFG): forward_with_cfg == u + s (c - u) of two plain forwards."""
+    net = make_big("DiT-B/2", dev, 1000, 0.1, 64)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(32, 4, 32, 32, generator=g).to(dev)
+    y = torch.randint(0, 1000, (32,), generator=g).to(dev)
+    ynull = torch.full((32,), 1000, device=dev)
+    t = torch.full((64,), 0.45, device=dev)
+    v = net.forward_with_cfg(t, torch.cat([x, x]), torch.cat([y, ynull]), cfg_scale=1.5)
+    c = net(t[:32], x, y)
+    u = net(t[:32], x, ynull)
+    assert rel_l2(v[:32].cpu(), (u + 1.5 * (c - u)).cpu()) < 1e-5
+    assert torch.equal(v[:32], v[32:])
+    # y=None selects the null class row (models/DiT.py:259-260)
+    assert torch.equal(net(t[:32], x), u)
+    # Heun-25 with CFG (configs[2] solver): 48 NFE, finite
+    out = lfm_b200.karras_sample(net, torch.cat([x, x]), 25, clip_denoised=False,
+                                 model_kwargs=dict(y=torch.cat([y, ynull]), cfg_scale=1.5), sigma_min=1e-5, sigma_max=1.0,
+                                 sampler="heun")
+    assert net.last_stats["nfe"] == 48 and torch.isfinite(out).all() and torch.equal(out[:32], out[32:])

@@ -1,0 +1,121 @@
+"""Host-side logic of the drop-in boundary (no GPU): state-dict surface, time grids, RNG-free helpers,
+the world_size-2 gather layout on gloo, and that the product refuses to run on CPU."""
+import os
+import types
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import lfm_b200
+from lfm_b200 import dist as ldist
+from lfm_b200.synthetic import synthetic_state_dict
+from oracle import dit as odit
+from oracle import solvers as osol
+
+
+def _mini(**kw):
+    args = dict(img_resolution=32, patch_size=2, in_channels=4, hidden_size=256, depth=2, num_heads=4, label_dropout=0.1,
+                num_classes=10)
+    args.update(kw)
+    return lfm_b200.DiT(**args)
+
+
+def test_state_dict_surface_matches_reference_keys():
+    # oracle.param_shapes is pinned to the reference by oracle/make_goldens.py (load_state_dict strict=True)
+    net = _mini()
+    cfg = odit.DiTConfig(hidden_size=256, depth=2, num_heads=4, label_dropout=0.1, num_classes=10)
+    want = odit.param_shapes(cfg)
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert got == want
+    assert list(got) == list(want)  # same registration order
+    with torch.device("meta"):
+        big = lfm_b200.DiT_models["DiT-L/2"](img_resolution=32, in_channels=4, label_dropout=0.0, num_classes=1)
+    assert len(big.state_dict()) == 252
+
+
+def test_reference_init_is_degenerate_and_synthetic_is_not():
+    net = _mini()
+    assert float(net.final_layer.linear.weight.abs().max()) == 0.0          # models/DiT.py:225-228
+    assert float(net.blocks[0].adaLN_modulation[1].weight.abs().max()) == 0.0
+    sd = synthetic_state_dict(net, 5)
+    ref = odit.synthetic_state_dict(odit.DiTConfig(hidden_size=256, depth=2, num_heads=4, label_dropout=0.1,
+                                                   num_classes=10), 5)
+    assert all(torch.equal(sd[k], ref[k]) for k in ref)
+    net.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError):
+        bad = dict(sd)
+        bad.pop("pos_embed")
+        net.load_state_dict(bad, strict=True)
+
+
+def test_checkpoint_prefix_strip_roundtrip():
+    # test_flow_latent.py:140-141 strips the 7-char "module." prefix before load_state_dict(strict=True)
+    net = _mini()
+    sd = synthetic_state_dict(net, 2)
+    ckpt = {"module." + k: v for k, v in sd.items()}
+    for key in list(ckpt.keys()):
+        ckpt[key[7:]] = ckpt.pop(key)
+    net.load_state_dict(ckpt, strict=True)
+
+
+def test_euler_time_grid_matches_oracle_restatement():
+    for h in (0.5, 0.1, 0.05, 0.02, 0.01, 1 / 3, 0.3):
+        a, b = lfm_b200.euler_time_grid(h), osol.tdq_euler_grid(h)
+        assert torch.equal(a, b)
+    assert len(lfm_b200.euler_time_grid(0.02)) == 51
+
+
+def test_no_cpu_path():
+    net = _mini()
+    x = torch.randn(2, 4, 32, 32)
+    with pytest.raises(RuntimeError):
+        net(torch.tensor(0.5), x)
+    with pytest.raises(RuntimeError):
+        lfm_b200.karras_sample(net, x, 4, clip_denoised=False, sampler="euler", sigma_min=1e-5, sigma_max=1.0)
+    with pytest.raises(NotImplementedError):
+        lfm_b200.karras_sample(net, x, 4, clip_denoised=True, sampler="euler")
+    with pytest.raises(NotImplementedError):
+        lfm_b200.create_network(types.SimpleNamespace(use_origin_adm=True))
+
+
+def test_create_network_factory():
+    cfg = types.SimpleNamespace(use_origin_adm=False, model_type="DiT-B/2", image_size=256, f=8, num_in_channels=4,
+                                label_dropout=0.1, num_classes=1000)
+    with torch.device("meta"):
+        net = lfm_b200.create_network(cfg)
+    assert net.hidden_size == 768 and net.depth == 12 and net.table_rows == 1001 and net.img_resolution == 32
+
+
+def test_ddp_index_helpers():
+    assert ldist.total_samples(50000, 64, 8) == 50176       # test_flow_latent_ddp.py:116-123
+    assert ldist.file_index(3, 8, 5, 512) == 3 * 8 + 5 + 512  # :138
+    assert ldist.rank_seed(42, 3) == 45
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    r, w, _ = ldist.init_from_env("gloo")
+    x = torch.arange(3 * 2, dtype=torch.float32).reshape(3, 2) + 100 * r   # 3 "images" per rank
+    out = ldist.all_gather_batch(x)
+    q.put((r, out.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_layout_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # image j of rank r lands at j * world + r (the reference's file index, test_flow_latent_ddp.py:138)
+    want = [[0, 1], [100, 101], [2, 3], [102, 103], [4, 5], [104, 105]]
+    assert res[0] == want and res[1] == want
