@@ -107,9 +107,9 @@ def build_model(device):
 
 
 def time_dominant_kernel(device, peaks, iters=20):
-    """Roofline of the dominant kernel: the tcgen05 GEMM, on its largest instance in the network
-    (mlp.fc1 + bias + GELU: M = 64*256, N = 4096, K = 1024), timed with CUDA events on the launching stream.
-    Operands + output = 176 MB > the 126 MB L2."""
+    """Roofline of the dominant kernel: the CTA-pair tcgen05 GEMM (gemm2_bf16_tcgen05), on its largest instance
+    in the network (mlp.fc1 + bias + GELU: M = 64*256, N = 4096, K = 1024), timed with CUDA events on the
+    launching stream.  Operands + output = 176 MB > the 126 MB L2."""
     from lfm_b200 import _lib
     lib = _lib.load()
     M, N, K = BATCH * 256, 4096, 1024
@@ -120,7 +120,7 @@ def time_dominant_kernel(device, peaks, iters=20):
     s = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
     def run():
-        rc = lib.lfm_dbg_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), None, 0, 256, M, N, K, 1, 256, s)
+        rc = lib.lfm_dbg_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), None, 0, 256, M, N, K, 1, 512, s)
         assert rc == 0, _lib.last_error()
     for _ in range(3):
         run()
@@ -138,7 +138,7 @@ def time_dominant_kernel(device, peaks, iters=20):
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("gemm_fc1_dram_bytes_per_launch")
-    return {"bound": "tensor", "kernel": "gemm_bf16_tcgen05<256,EPI_BIAS_GELU_BF16> M=16384 N=4096 K=1024",
+    return {"bound": "tensor", "kernel": "gemm2_bf16_tcgen05<EPI_BIAS_GELU_BF16> (cta_group::2, 256x256 tile) M=16384 N=4096 K=1024",
             "achieved": round(achieved, 1), "peak": peaks["burst"], "unit": "TFLOP/s", "frac": round(achieved / peaks["burst"], 4),
             "traffic": traffic, "us_per_launch": round(ms * 1e3, 2), "peak_source": peaks["source"] + ", burst (kernel timed alone)"}
 

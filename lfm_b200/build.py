@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "lfm_api.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("lfm_api.cu", "common.cuh", "gemm.cuh", "attention.cuh", "kernels.cuh")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [
     os.path.join(os.path.dirname(HERE), "include", "lfm_b200.h")]
 OUT = os.path.join(HERE, "liblfm_b200.so")
 

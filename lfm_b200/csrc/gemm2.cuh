@@ -1,0 +1,345 @@
+// lfm_b200 - 2-CTA (cta_group::2) persistent tcgen05 GEMM: the workhorse for the DiT linear layers.
+//
+//   C[M, N] = A[M, K] * W[N, K]^T,  one 256 x 256 output tile per CTA PAIR (thread-block cluster of 2).
+//
+// Why pairs: with one CTA per 128 x 256 tile every SM pulls 48 KB per 64-wide K slab from L2 (94 B/clk/SM at
+// full tensor rate) and the measured tensor-pipe utilisation tops out at ~65 % (profiles/r1_gemm_full.md).  In
+// cta_group::2 mode each CTA stages only its own 128 rows of A and HALF of the W tile (128 of the 256 rows); the
+// tensor cores of both SMs read the two halves from both shared memories.  32 KB per slab per SM (64 B/clk), and
+// the freed shared memory deepens the TMA ring from 4 to 6 stages.
+//
+// Roles per CTA (384 threads): warp 0 = TMA producer (own A rows + own half of W; completion bytes are posted
+// on the LEADER CTA's mbarrier), warp 1 = MMA issuer (leader CTA only, tcgen05.mma.cta_group::2, M = 256),
+// warp 2 = TMEM allocator, warps 4..11 = epilogue: 8 warps, TMEM lane quadrant = warp % 4, column half =
+// (warp - 4) / 4, software-pipelined tcgen05.ld (next chunk in flight while the current one is processed).
+// Accumulator double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace lfm {
+
+constexpr int kG2Threads = 384;
+constexpr int kG2BlockN = 256;
+constexpr int kG2Stages = 6;
+constexpr int kG2ABytes = 128 * 64 * 2;
+constexpr int kG2BBytes = 128 * 64 * 2;  // this CTA's half of the W tile
+constexpr int kG2StageBytes = kG2ABytes + kG2BBytes;
+constexpr int kG2StagingBytes = 8 * 4096;  // one 32-row x 128-byte tile per epilogue warp
+constexpr int kG2SmemBytes = kG2Stages * kG2StageBytes + 1024 /*barriers*/ + kG2StagingBytes + 1024 /*align slack*/;
+
+LFM_DEVICE uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+LFM_DEVICE void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+LFM_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// TMA load issued by either CTA of the pair; the transaction bytes are credited to the LEADER CTA's mbarrier
+// (shared::cluster address of the executing CTA with the CTA-rank bit cleared).
+LFM_DEVICE void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1)
+        : "memory");
+}
+LFM_DEVICE void umma_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit -> arrive on the mbarrier at this offset in BOTH CTAs of the pair
+LFM_DEVICE void umma_commit_2cta(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+template <uint32_t kCols>
+LFM_DEVICE void tmem_alloc_2cta(uint32_t* smem_result) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+LFM_DEVICE void tmem_dealloc_2cta(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// TMA reduce-add shared -> global (fp32 tensor map): global[tile] += smem[tile], performed at L2.
+LFM_DEVICE void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// Epilogue math for 32 accumulator columns of one row -> f[32] (bias, GELU, gate).
+template <int EPI>
+LFM_DEVICE void epilogue_math(const uint32_t* v, float* f, const GemmEpi& ep, int n0, int N, const float* gate_row) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (n0 >= N) return;  // warp-uniform; the TMA store clips these columns anyway
+    if (ep.bias != nullptr) {
+        const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (n0 + j * 4 < N) {
+                const float4 b4 = __ldg(bp + j);
+                f[4 * j + 0] += b4.x;
+                f[4 * j + 1] += b4.y;
+                f[4 * j + 2] += b4.z;
+                f[4 * j + 3] += b4.w;
+            }
+        }
+    }
+    if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+    }
+    if (EPI == EPI_GATE_RESID_F32 && gate_row != nullptr) {
+        const float4* gp = reinterpret_cast<const float4*>(gate_row + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (n0 + j * 4 < N) {
+                const float4 g4 = __ldg(gp + j);
+                f[4 * j + 0] *= g4.x;
+                f[4 * j + 1] *= g4.y;
+                f[4 * j + 2] *= g4.z;
+                f[4 * j + 3] *= g4.w;
+            }
+        }
+    }
+}
+
+// Write this lane's row segment (128 bytes = 8 x 16 B) into the warp's 32-row staging tile, 128B-swizzled
+// (16-byte chunk j of row r lives at chunk j ^ (r & 7)): conflict-free, and the layout TMA expects.
+LFM_DEVICE void stage_row_f32(uint8_t* stg, int lane, const float* f) {
+    uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+}
+LFM_DEVICE void stage_row_bf16_half(uint8_t* stg, int lane, const float* f, int half) {  // 32 values -> chunks 4*half..
+    uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+        o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+        o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+        o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+        *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ (lane & 7)) << 4)) = o;
+    }
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
+gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], box {64, 128}
+                   const __grid_constant__ CUtensorMap tmap_b,   // W [N, K], box {64, 128}
+                   const __grid_constant__ CUtensorMap tmap_out, // out [M, ldo]: box {128 bytes, 32 rows}, 128B swizzle
+                   int M, int N, int K, GemmEpi ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kG2Stages * kG2ABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kG2Stages * kG2StageBytes);
+    uint64_t* full_bar = bars;                        // [stages] (used in the leader CTA only)
+    uint64_t* empty_bar = bars + kG2Stages;           // [stages] per CTA, signalled by the leader's multicast commit
+    uint64_t* tmem_full = bars + 2 * kG2Stages;       // [2] per CTA, multicast commit
+    uint64_t* tmem_empty = bars + 2 * kG2Stages + 2;  // [2] leader only: 16 epilogue warps (8 per CTA) arrive
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kG2Stages + 4);
+    uint8_t* smem_stage = smem + kG2Stages * kG2StageBytes + 1024;  // 8 x 4 KB epilogue staging tiles (1024-aligned)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    const int n_blocks = (N + kG2BlockN - 1) / kG2BlockN;
+    const int m_blocks = (M + 255) / 256;
+    const int num_tiles = m_blocks * n_blocks;
+    const int num_kb = K / 64;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        prefetch_tmap(&tmap_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kG2Stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 16);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) tmem_alloc_2cta<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();  // barrier inits + TMEM allocation visible in both CTAs before any remote traffic
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+                const int row_a = m_blk * 256 + static_cast<int>(rank) * 128;
+                const int row_b = n_blk * kG2BlockN + static_cast<int>(rank) * 128;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kG2StageBytes);
+                    tma_load_2d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * 64, row_a);
+                    tma_load_2d_2sm(smem_b + stage * kG2BBytes, &tmap_b, &full_bar[stage], kb * 64, row_b);
+                    if (++stage == kG2Stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA, one thread) =====================
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, kG2BlockN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * kG2BlockN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + stage * kG2ABytes), 16, 1024);
+                    const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * kG2BBytes), 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_2cta(&empty_bar[stage]);
+                    if (kb == num_kb - 1) umma_commit_2cta(&tmem_full[acc]);
+                    if (++stage == kG2Stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: 8 warps, 128 rows x (2 x 128 columns) =====================
+        // TMEM -> registers -> (bias / GELU / gate) -> swizzled smem staging tile -> TMA store, or TMA reduce-add
+        // for the gated residual (x += g * (acc + b) is applied at L2: the SM never reads x).
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        uint8_t* stg = smem_stage + (warp - 4) * 4096;
+        constexpr bool kBf16Out = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+            const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;  // first row of this warp
+            const int row = row0 + lane;
+            const int nbase = n_blk * kG2BlockN + half * 128;
+            const float* gate_row = nullptr;
+            if (EPI == EPI_GATE_RESID_F32)
+                gate_row = ep.gate + static_cast<size_t>((row < M ? row : M - 1) / ep.rows_per_sample) * ep.gate_stride;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kG2BlockN + half * 128;
+            uint32_t va[32], vb[32];
+            float f[32];
+            tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll
+            for (int c = 0; c < 4; c += 2) {
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
+                epilogue_math<EPI>(va, f, ep, nbase + c * 32, N, gate_row);
+                // staging tile free again? (the previous TMA op of this warp has finished READING it)
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+                if (kBf16Out) {
+                    stage_row_bf16_half(stg, lane, f, 0);
+                } else {
+                    stage_row_f32(stg, lane, f);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && nbase + c * 32 < N) {
+                        if (EPI == EPI_GATE_RESID_F32)
+                            tma_reduce_add_2d(&tmap_out, stg, nbase + c * 32, row0);
+                        else
+                            tma_store_2d(&tmap_out, stg, nbase + c * 32, row0);
+                        tma_store_commit();
+                    }
+                }
+                tmem_ld_wait();
+                if (c + 2 < 4) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
+                epilogue_math<EPI>(vb, f, ep, nbase + (c + 1) * 32, N, gate_row);
+                if (kBf16Out) {
+                    stage_row_bf16_half(stg, lane, f, 1);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && nbase + c * 32 < N) {
+                        tma_store_2d(&tmap_out, stg, nbase + c * 32, row0);  // 64 bf16 columns x 32 rows
+                        tma_store_commit();
+                    }
+                } else {
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                    stage_row_f32(stg, lane, f);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && nbase + (c + 1) * 32 < N) {
+                        if (EPI == EPI_GATE_RESID_F32)
+                            tma_reduce_add_2d(&tmap_out, stg, nbase + (c + 1) * 32, row0);
+                        else
+                            tma_store_2d(&tmap_out, stg, nbase + (c + 1) * 32, row0);
+                        tma_store_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // leader's barrier
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+        if (lane == 0) tma_store_wait<0>();  // all global writes of this warp are complete before the CTA exits
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // nobody leaves while the peer may still read this CTA's smem / signal its barriers
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta<512>(tmem_base);
+    }
+}
+
+}  // namespace lfm

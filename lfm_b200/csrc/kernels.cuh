@@ -116,49 +116,99 @@ patch_embed_kernel(const float* __restrict__ x, int x_rows, const float* __restr
 // ------------------------------------------------------------------------------------------------
 // K5/K9: LayerNorm (no affine, eps 1e-6) + adaLN modulate, fp32 tokens -> bf16 GEMM operand.
 //   y = (x - mean) * rstd * (1 + scale[b]) + shift[b]        (reference models/DiT.py:20-21,119,121,129-130)
-// One warp per token row; the row lives in registers (D <= 1536).
-__global__ void __launch_bounds__(256)
+// HBM-bound (reads 4 B, writes 2 B per element).  Persistent blocks; the token rows stream through a 4-stage
+// shared-memory ring filled by 1-D bulk async copies (cp.async.bulk + mbarrier transaction bytes), 8 rows per
+// stage, so loads of later rows are always in flight while the 8 warps normalise the current ones.
+// One warp per row, two-pass statistics in registers, coalesced bf16 stores.
+constexpr int kLnRows = 8;    // rows per stage (= warps per block)
+constexpr int kLnStages = 4;
+
+LFM_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int NV>  // NV = D / 128 float4 per lane
+__global__ void __launch_bounds__(256, 1)
 ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ shift,
-                   const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M, int D) {
-    constexpr int MAXV = 12;
+                   const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M) {
+    constexpr int D = NV * 128;
+    constexpr uint32_t kStageBytes = kLnRows * D * 4;
+    extern __shared__ __align__(128) uint8_t ln_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kLnStages];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + warp;
-    if (row >= M) return;
-    const int nv = D / 128;
-    const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-    float4 v[MAXV];
-    float s = 0.f;
-#pragma unroll
-    for (int m = 0; m < MAXV; ++m) {
-        if (m < nv) {
-            v[m] = xp[m * 32 + lane];
-            s += (v[m].x + v[m].y) + (v[m].z + v[m].w);
-        }
+    const int num_tiles = (M + kLnRows - 1) / kLnRows;
+    // contiguous tile range per block (keeps one block inside as few samples as possible)
+    const int per = (num_tiles + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * per;
+    const int t_end = min(num_tiles, t_begin + per);
+    const int my_tiles = max(0, t_end - t_begin);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kLnStages; ++s) mbar_init(&full_bar[s], 1);
+        fence_barrier_init();
+        fence_proxy_async();
     }
-    const float mean = warp_sum(s) / static_cast<float>(D);
-    float ss = 0.f;
+    __syncthreads();
+    auto issue = [&](int i) {  // thread 0: load tile t_begin + i into stage i % kLnStages
+        const int tile = t_begin + i;
+        const int rows = min(kLnRows, M - tile * kLnRows);
+        const uint32_t bytes = static_cast<uint32_t>(rows) * D * 4;
+        uint64_t* bar = &full_bar[i % kLnStages];
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_load_1d(ln_smem + (i % kLnStages) * kStageBytes, x + static_cast<size_t>(tile) * kLnRows * D, bytes, bar);
+    };
+    if (threadIdx.x == 0)
+        for (int i = 0; i < kLnStages && i < my_tiles; ++i) issue(i);
+
+    for (int i = 0; i < my_tiles; ++i) {
+        const int stage = i % kLnStages;
+        const uint32_t parity = (i / kLnStages) & 1;
+        const int row = (t_begin + i) * kLnRows + warp;
+        const bool ok = row < M;
+        // modulation vectors first: their L2 latency overlaps the wait for the row data
+        float4 sh[NV], sc[NV];
+        if (ok) {
+            const size_t boff = static_cast<size_t>(row / rows_per_sample) * mod_stride;
+            const float4* shp = reinterpret_cast<const float4*>(shift + boff);
+            const float4* scp = reinterpret_cast<const float4*>(scale + boff);
 #pragma unroll
-    for (int m = 0; m < MAXV; ++m) {
-        if (m < nv) {
-            const float a = v[m].x - mean, b = v[m].y - mean, c = v[m].z - mean, d = v[m].w - mean;
-            ss += (a * a + b * b) + (c * c + d * d);
+            for (int m = 0; m < NV; ++m) {
+                sh[m] = __ldg(shp + m * 32 + lane);
+                sc[m] = __ldg(scp + m * 32 + lane);
+            }
         }
-    }
-    const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + 1e-6f);
-    const size_t boff = static_cast<size_t>(row / rows_per_sample) * mod_stride;
-    const float4* shp = reinterpret_cast<const float4*>(shift + boff);
-    const float4* scp = reinterpret_cast<const float4*>(scale + boff);
-    uint2* yp = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+        mbar_wait(&full_bar[stage], parity);
+        if (ok) {
+            const float4* xp = reinterpret_cast<const float4*>(ln_smem + stage * kStageBytes + warp * D * 4);
+            float4 v[NV];
+            float s = 0.f;
 #pragma unroll
-    for (int m = 0; m < MAXV; ++m) {
-        if (m < nv) {
-            const float4 sh = __ldg(shp + m * 32 + lane), sc = __ldg(scp + m * 32 + lane);
-            const float a = fmaf((v[m].x - mean) * rstd, 1.f + sc.x, sh.x);
-            const float b = fmaf((v[m].y - mean) * rstd, 1.f + sc.y, sh.y);
-            const float c = fmaf((v[m].z - mean) * rstd, 1.f + sc.z, sh.z);
-            const float d = fmaf((v[m].w - mean) * rstd, 1.f + sc.w, sh.w);
-            yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+            for (int m = 0; m < NV; ++m) {
+                v[m] = xp[m * 32 + lane];
+                s += (v[m].x + v[m].y) + (v[m].z + v[m].w);
+            }
+            const float mean = warp_sum(s) / static_cast<float>(D);
+            float ss = 0.f;
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+                const float a = v[m].x - mean, b = v[m].y - mean, c = v[m].z - mean, d = v[m].w - mean;
+                ss += (a * a + b * b) + (c * c + d * d);
+            }
+            const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + 1e-6f);
+            uint2* yp = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+                const float a = fmaf((v[m].x - mean) * rstd, 1.f + sc[m].x, sh[m].x);
+                const float b = fmaf((v[m].y - mean) * rstd, 1.f + sc[m].y, sh[m].y);
+                const float c = fmaf((v[m].z - mean) * rstd, 1.f + sc[m].z, sh[m].z);
+                const float d = fmaf((v[m].w - mean) * rstd, 1.f + sc[m].w, sh[m].w);
+                yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+            }
         }
+        __syncthreads();  // every warp has consumed this stage
+        if (threadIdx.x == 0 && i + kLnStages < my_tiles) issue(i + kLnStages);
     }
 }
 

@@ -14,6 +14,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "kernels.cuh"
 
 using namespace lfm;
@@ -66,6 +67,21 @@ static bool make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint
     return r == CUDA_SUCCESS;
 }
 
+// Output tile map for the TMA-store epilogue: row-major [rows, cols] (bf16 or fp32), box = 128 bytes x 32 rows.
+static bool make_tmap_out(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, bool is_f32) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return false;
+    const uint64_t esz = is_f32 ? 4 : 2;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * esz};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel launch helpers
 
@@ -87,8 +103,38 @@ static cudaError_t launch_gemm_inst(cudaStream_t s, const CUtensorMap& ta, const
     return cudaGetLastError();
 }
 
+// 2-CTA pair kernel (256 x 256 tile per cluster of two CTAs)
+template <int EPI>
+static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb,
+                                     const CUtensorMap& tout, int M, int N, int K, const GemmEpi& ep) {
+    static bool attr_set = false;
+    auto kern = gemm2_bf16_tcgen05<EPI>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2SmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tiles = ((M + 255) / 256) * ((N + kG2BlockN - 1) / kG2BlockN);
+    int clusters = g_num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    kern<<<2 * clusters, kG2Threads, kG2SmemBytes, s>>>(ta, tb, tout, M, N, K, ep);
+    return cudaGetLastError();
+}
+
+// block_n: 128 / 256 = one CTA per 128 x block_n tile; kGemmPair (512) = CTA pair per 256 x 256 tile
+constexpr int kGemmPair = 512;
+static inline uint32_t weight_box_rows(int block_n) { return block_n == kGemmPair ? 128u : static_cast<uint32_t>(block_n); }
+
 static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-                               int epi, int block_n, const GemmEpi& ep) {
+                               int epi, int block_n, const GemmEpi& ep, const CUtensorMap* tout = nullptr) {
+    if (block_n == kGemmPair) {
+        if (tout == nullptr) return cudaErrorInvalidValue;
+        if (epi == EPI_BIAS_BF16) return launch_gemm2_inst<EPI_BIAS_BF16>(s, ta, tb, *tout, M, N, K, ep);
+        if (epi == EPI_BIAS_GELU_BF16) return launch_gemm2_inst<EPI_BIAS_GELU_BF16>(s, ta, tb, *tout, M, N, K, ep);
+        if (epi == EPI_GATE_RESID_F32) return launch_gemm2_inst<EPI_GATE_RESID_F32>(s, ta, tb, *tout, M, N, K, ep);
+        if (epi == EPI_BIAS_F32) return launch_gemm2_inst<EPI_BIAS_F32>(s, ta, tb, *tout, M, N, K, ep);
+        return cudaErrorInvalidValue;
+    }
 #define LFM_GEMM_CASE(BN, E) \
     if (block_n == BN && epi == E) return launch_gemm_inst<BN, E>(s, ta, tb, M, N, K, ep);
     LFM_GEMM_CASE(256, EPI_BIAS_BF16)
@@ -117,6 +163,34 @@ static cudaError_t launch_attention_inst(cudaStream_t s, const CUtensorMap& tq, 
     const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e), head_dim = 64
     kern<<<dim3(2, H, B), kAttnThreads, attn_smem_bytes<P_TMEM>(), s>>>(tq, tkv, out, D, scale_log2e, dbg_s);
     return cudaGetLastError();
+}
+
+template <int NV>
+static cudaError_t launch_ln_inst(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
+                                  int mod_stride, int rows_per_sample, int M) {
+    static bool attr_set = false;
+    const int smem = kLnStages * kLnRows * NV * 128 * 4;
+    auto kern = ln_modulate_kernel<NV>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tiles = (M + kLnRows - 1) / kLnRows;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    kern<<<grid, 256, smem, s>>>(x, y, shift, scale, mod_stride, rows_per_sample, M);
+    return cudaGetLastError();
+}
+static cudaError_t launch_ln(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
+                             int mod_stride, int rows_per_sample, int M, int D) {
+    switch (D / 128) {
+        case 2: return launch_ln_inst<2>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
+        case 3: return launch_ln_inst<3>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
+        case 6: return launch_ln_inst<6>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
+        case 8: return launch_ln_inst<8>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
+        case 9: return launch_ln_inst<9>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 static inline unsigned blocks_for(size_t n, int threads = 256) { return static_cast<unsigned>((n + threads - 1) / threads); }
@@ -165,6 +239,7 @@ struct lfm_ctx {
     float *x_tok = nullptr, *mod = nullptr, *tfreq = nullptr, *h1 = nullptr, *v_net = nullptr;
     __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hmid = nullptr, *c_silu = nullptr;
     CUtensorMap tm_xn, tm_attn, tm_hmid, tm_csilu, tm_qkv_q, tm_qkv_kv;
+    CUtensorMap tmo_qkv, tmo_hmid, tmo_xtok;  // TMA-store epilogue targets
 
     // solver state
     cudaStream_t stream = nullptr;
@@ -225,8 +300,11 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     if (desc->patch_size != 2) return fail(nullptr, "lfm_create: only patch_size 2 is implemented (got %d)", desc->patch_size);
     if (desc->img_resolution != 32)
         return fail(nullptr, "lfm_create: only 32x32 latents (256 tokens) are implemented (got %d)", desc->img_resolution);
-    if (desc->hidden_size % 128 != 0 || desc->hidden_size > 1536)
-        return fail(nullptr, "lfm_create: hidden_size must be a multiple of 128 and <= 1536 (got %d)", desc->hidden_size);
+    {
+        const int nv = desc->hidden_size / 128;
+        if (desc->hidden_size % 128 != 0 || !(nv == 2 || nv == 3 || nv == 6 || nv == 8 || nv == 9))
+            return fail(nullptr, "lfm_create: hidden_size must be one of 256, 384, 768, 1024, 1152 (got %d)", desc->hidden_size);
+    }
     if (desc->num_heads * 64 != desc->hidden_size)
         return fail(nullptr, "lfm_create: head_dim must be 64 (hidden %d, heads %d)", desc->hidden_size, desc->num_heads);
     if (desc->mlp_hidden % 64 != 0) return fail(nullptr, "lfm_create: mlp_hidden must be a multiple of 64");
@@ -342,7 +420,7 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
 
 static int pick_bn(int N, const char* env, int dflt) {
     int bn = env_int(env, dflt);
-    if (bn != 128 && bn != 256) bn = dflt;
+    if (bn != 128 && bn != 256 && bn != kGemmPair) bn = dflt;
     return bn;
 }
 
@@ -385,10 +463,11 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
     if (dev_alloc(ctx, &ctx->step_state, 1)) return 1;
     CUDA_OK(cudaMallocHost(&ctx->ratio_host, 64));
 
-    ctx->bn_qkv = pick_bn(3 * D, "LFM_BN_QKV", (3 * D) % 256 == 0 ? 256 : 128);
-    ctx->bn_proj = pick_bn(D, "LFM_BN_PROJ", D % 256 == 0 ? 256 : 128);
-    ctx->bn_fc1 = pick_bn(Hd, "LFM_BN_FC1", Hd % 256 == 0 ? 256 : 128);
-    ctx->bn_fc2 = pick_bn(D, "LFM_BN_FC2", D % 256 == 0 ? 256 : 128);
+    // default: the CTA-pair kernel for every token-level GEMM (LFM_BN_* = 128 / 256 selects the 1-CTA kernel)
+    ctx->bn_qkv = pick_bn(3 * D, "LFM_BN_QKV", kGemmPair);
+    ctx->bn_proj = pick_bn(D, "LFM_BN_PROJ", kGemmPair);
+    ctx->bn_fc1 = pick_bn(Hd, "LFM_BN_FC1", kGemmPair);
+    ctx->bn_fc2 = pick_bn(D, "LFM_BN_FC2", kGemmPair);
     ctx->bn_mod = 256;
     bool ok = true;
     ok &= make_tmap_bf16(&ctx->tm_xn, ctx->xn, M, D, 128);
@@ -398,11 +477,14 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
     ok &= make_tmap_bf16(&ctx->tm_qkv_q, ctx->qkv, M, 3 * D, 128);
     ok &= make_tmap_bf16(&ctx->tm_qkv_kv, ctx->qkv, M, 3 * D, 256);
     ok &= make_tmap_bf16(&ctx->tm_wmod, ctx->w_mod, ctx->Nmod, D, ctx->bn_mod);
+    ok &= make_tmap_out(&ctx->tmo_qkv, ctx->qkv, M, 3 * D, false);
+    ok &= make_tmap_out(&ctx->tmo_hmid, ctx->hmid, M, Hd, false);
+    ok &= make_tmap_out(&ctx->tmo_xtok, ctx->x_tok, M, D, true);
     for (auto& b : ctx->blk) {
-        ok &= make_tmap_bf16(&b.tm_qkv, b.w_qkv, 3 * D, D, ctx->bn_qkv);
-        ok &= make_tmap_bf16(&b.tm_proj, b.w_proj, D, D, ctx->bn_proj);
-        ok &= make_tmap_bf16(&b.tm_fc1, b.w_fc1, Hd, D, ctx->bn_fc1);
-        ok &= make_tmap_bf16(&b.tm_fc2, b.w_fc2, D, Hd, ctx->bn_fc2);
+        ok &= make_tmap_bf16(&b.tm_qkv, b.w_qkv, 3 * D, D, weight_box_rows(ctx->bn_qkv));
+        ok &= make_tmap_bf16(&b.tm_proj, b.w_proj, D, D, weight_box_rows(ctx->bn_proj));
+        ok &= make_tmap_bf16(&b.tm_fc1, b.w_fc1, Hd, D, weight_box_rows(ctx->bn_fc1));
+        ok &= make_tmap_bf16(&b.tm_fc2, b.w_fc2, D, Hd, weight_box_rows(ctx->bn_fc2));
     }
     if (!ok) return fail(ctx, "lfm_finalize: cuTensorMapEncodeTiled failed");
     ctx->max_rows = R;
@@ -442,11 +524,11 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
     for (int l = 0; l < L; ++l) {
         BlockW& b = ctx->blk[l];
         const float* mb = ctx->mod + (size_t)l * 6 * D;  // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
-        ln_modulate_kernel<<<(M + 7) / 8, 256, 0, s>>>(ctx->x_tok, ctx->xn, mb, mb + D, Nmod, T, M, D);
-        LAUNCH_OK();
+        CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb, mb + D, Nmod, T, M, D));
+        ctx->launches++;
         {
             GemmEpi ep{b.b_qkv, ctx->qkv, 3 * D, nullptr, 0, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep));
+            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv));
             ctx->launches++;
         }
         if (ctx->attn_variant == 0)
@@ -456,19 +538,19 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         ctx->launches++;
         {
             GemmEpi ep{b.b_proj, ctx->x_tok, D, mb + 2 * D, Nmod, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep));
+            CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok));
             ctx->launches++;
         }
-        ln_modulate_kernel<<<(M + 7) / 8, 256, 0, s>>>(ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D);
-        LAUNCH_OK();
+        CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D));
+        ctx->launches++;
         {
             GemmEpi ep{b.b_fc1, ctx->hmid, Hd, nullptr, 0, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_fc1, M, Hd, D, EPI_BIAS_GELU_BF16, ctx->bn_fc1, ep));
+            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_fc1, M, Hd, D, EPI_BIAS_GELU_BF16, ctx->bn_fc1, ep, &ctx->tmo_hmid));
             ctx->launches++;
         }
         {
             GemmEpi ep{b.b_fc2, ctx->x_tok, D, mb + 5 * D, Nmod, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep));
+            CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep, &ctx->tmo_xtok));
             ctx->launches++;
         }
     }
@@ -898,7 +980,8 @@ extern "C" int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float*
                             void* stream) {
     lfm_ctx* ctx = nullptr;
     if (K % 64 != 0 || N % 8 != 0) return fail(ctx, "lfm_dbg_gemm: K must be a multiple of 64 and N of 8");
-    if (block_n != 128 && block_n != 256) return fail(ctx, "lfm_dbg_gemm: block_n must be 128 or 256");
+    if (block_n != 128 && block_n != 256 && block_n != kGemmPair)
+        return fail(ctx, "lfm_dbg_gemm: block_n must be 128, 256 or 512 (CTA pair)");
     if (g_num_sms == 0) {
         int dev = 0;
         CUDA_OK(cudaGetDevice(&dev));
@@ -907,10 +990,12 @@ extern "C" int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float*
         g_num_sms = prop.multiProcessorCount;
     }
     CUtensorMap ta, tb;
-    if (!make_tmap_bf16(&ta, a_bf16, M, K, 128) || !make_tmap_bf16(&tb, w_bf16, N, K, block_n))
+    if (!make_tmap_bf16(&ta, a_bf16, M, K, 128) || !make_tmap_bf16(&tb, w_bf16, N, K, weight_box_rows(block_n)))
         return fail(ctx, "lfm_dbg_gemm: tensor map encode failed");
     GemmEpi ep{bias, out, N, gate, gate_stride, rows_per_sample > 0 ? rows_per_sample : 1};
-    CUDA_OK(launch_gemm(static_cast<cudaStream_t>(stream), ta, tb, M, N, K, epi, block_n, ep));
+    CUtensorMap tout;
+    if (!make_tmap_out(&tout, out, M, N, epi >= 2)) return fail(ctx, "lfm_dbg_gemm: output tensor map encode failed");
+    CUDA_OK(launch_gemm(static_cast<cudaStream_t>(stream), ta, tb, M, N, K, epi, block_n, ep, &tout));
     return 0;
 }
 

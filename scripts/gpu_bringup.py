@@ -64,7 +64,10 @@ def group_gemm():
                                (256, 512, 1024, 0, 256), (512, 1024, 1024, 1, 256), (512, 1024, 4096, 2, 256),
                                (512, 1024, 4096, 2, 128), (64, 2048, 1024, 3, 256), (4, 1024, 256, 3, 256),
                                (256, 1152, 384, 0, 256), (256, 1152, 384, 0, 128), (16384, 3072, 1024, 0, 256),
-                               (16384, 1024, 1024, 2, 128)]:
+                               (16384, 1024, 1024, 2, 128),
+                               (256, 256, 64, 3, 512), (256, 512, 1024, 0, 512), (512, 1024, 1024, 1, 512),
+                               (512, 1024, 4096, 2, 512), (64, 2048, 1024, 3, 512), (768, 1152, 384, 0, 512),
+                               (16384, 3072, 1024, 0, 512), (16384, 1024, 4096, 2, 512), (16384, 4096, 1024, 1, 512)]:
         gemm_case(M, N, K, epi, bn)
 
 
@@ -199,7 +202,7 @@ def time_gemm(M, N, K, epi, bn, iters=20):
 def group_perf():
     for M in (16384, 32768, 4096):
         for (N, K, epi) in ((3072, 1024, 0), (1024, 1024, 2), (4096, 1024, 1), (1024, 4096, 2)):
-            for bn in (256, 128):
+            for bn in (512, 256):
                 time_gemm(M, N, K, epi, bn)
     # cuBLAS reference for the same shapes
     for (M, N, K) in ((16384, 3072, 1024), (16384, 1024, 1024), (16384, 4096, 1024), (16384, 1024, 4096)):
