@@ -1,0 +1,271 @@
+"""test_flow_latent.py-compatible sampling command line, running on liblfm_b200.so.
+
+    python -m lfm_b200.cli --exp celeb_f8_dit --dataset celeba_256 --model_type DiT-L/2 --image_size 256 --f 8 \
+        --num_in_channels 4 --num_out_channels 4 --num_classes 1 --label_dropout 0. --batch_size 64 \
+        --method euler --step_size 0.02 --epoch_id 475
+
+Same flags, defaults and modes as the reference (test_flow_latent.py:302-408): default "inference" (one batch ->
+image grid), ``--compute_nfe``, ``--measure_time``, ``--compute_fid`` (generation loop with the reference's file
+indexing; the FID statistic itself is the reference's pytorch_fid and is out of this build's scope).  Under
+``torchrun`` (RANK/WORLD_SIZE set) it behaves like test_flow_latent_ddp.py: one process per GPU, per-rank batches,
+seed = seed + rank, file index j * world + rank + total.
+
+Differences, all deliberate:
+  * the Karras path works (the reference's CLI raises NameError / TypeError there);
+  * ``--device`` exists; nothing is hard-coded to "cuda";
+  * ``--synthetic_init SEED`` runs without a checkpoint (seeded non-degenerate weights);
+  * without ``diffusers`` (not in this image) the VAE decode is skipped and latents are saved (``--no_decode``).
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+
+import numpy as np
+import torch
+
+
+def build_parser():
+    p = argparse.ArgumentParser("flow-matching parameters")
+    p.add_argument("--generator", type=str, default="determ", choices=["dummy", "determ", "determ-indiv"])
+    p.add_argument("--seed", type=int, default=42)
+    p.add_argument("--compute_fid", action="store_true", default=False)
+    p.add_argument("--compute_nfe", action="store_true", default=False)
+    p.add_argument("--measure_time", action="store_true", default=False)
+    p.add_argument("--epoch_id", type=int, default=1000)
+    p.add_argument("--n_sample", type=int, default=50000)
+    p.add_argument("--model_type", type=str, default="adm")
+    p.add_argument("--image_size", type=int, default=32)
+    p.add_argument("--f", type=int, default=8)
+    p.add_argument("--scale_factor", type=float, default=0.18215)
+    p.add_argument("--num_in_channels", type=int, default=3)
+    p.add_argument("--num_out_channels", type=int, default=3)
+    p.add_argument("--nf", type=int, default=256)
+    p.add_argument("--centered", action="store_false", default=True)
+    p.add_argument("--resamp_with_conv", type=bool, default=True)
+    p.add_argument("--num_res_blocks", type=int, default=2)
+    p.add_argument("--num_heads", type=int, default=4)
+    p.add_argument("--num_head_upsample", type=int, default=-1)
+    p.add_argument("--num_head_channels", type=int, default=-1)
+    p.add_argument("--attn_resolutions", nargs="+", type=int, default=(16,))
+    p.add_argument("--ch_mult", nargs="+", type=int, default=(1, 2, 2, 2))
+    p.add_argument("--label_dim", type=int, default=0)
+    p.add_argument("--augment_dim", type=int, default=0)
+    p.add_argument("--dropout", type=float, default=0.0)
+    p.add_argument("--num_classes", type=int, default=None)
+    p.add_argument("--label_dropout", type=float, default=0.0)
+    p.add_argument("--cfg_scale", type=float, default=1.0)
+    p.add_argument("--layout", action="store_true")
+    p.add_argument("--use_origin_adm", action="store_true")
+    p.add_argument("--use_scale_shift_norm", type=bool, default=True)
+    p.add_argument("--resblock_updown", type=bool, default=False)
+    p.add_argument("--use_new_attention_order", type=bool, default=False)
+    p.add_argument("--pretrained_autoencoder_ckpt", type=str, default="stabilityai/sd-vae-ft-mse")
+    p.add_argument("--output_log", type=str, default="")
+    p.add_argument("--exp", default="experiment_cifar_default")
+    p.add_argument("--real_img_dir", default="./pytorch_fid/cifar10_train_stat.npy")
+    p.add_argument("--dataset", default="cifar10")
+    p.add_argument("--num_steps", type=int, default=40)
+    p.add_argument("--batch_size", type=int, default=200)
+    p.add_argument("--use_karras_samplers", action="store_true", default=False)
+    p.add_argument("--atol", type=float, default=1e-5)
+    p.add_argument("--rtol", type=float, default=1e-5)
+    p.add_argument("--method", type=str, default="dopri5",
+                   choices=["dopri5", "dopri8", "adaptive_heun", "bosh3", "euler", "midpoint", "rk4", "heun", "multistep",
+                            "stochastic", "dpm"])
+    p.add_argument("--step_size", type=float, default=0.01)
+    p.add_argument("--perturb", action="store_true", default=False)
+    p.add_argument("--num_proc_node", type=int, default=1)
+    p.add_argument("--num_process_per_node", type=int, default=1)
+    p.add_argument("--node_rank", type=int, default=0)
+    p.add_argument("--local_rank", type=int, default=0)
+    p.add_argument("--master_address", type=str, default="127.0.0.1")
+    p.add_argument("--master_port", type=str, default="6000")
+    # additions
+    p.add_argument("--device", type=str, default=None, help="cuda:N (default: cuda:LOCAL_RANK)")
+    p.add_argument("--synthetic_init", type=int, default=None, metavar="SEED", help="seeded weights instead of a checkpoint")
+    p.add_argument("--no_decode", action="store_true", help="skip the VAE decode; save latents (.npy)")
+    p.add_argument("--out_dir", type=str, default=".")
+    p.add_argument("--measure_reps", type=int, default=300)
+    return p
+
+
+def load_model(args, device):
+    from . import create_network
+    from .synthetic import synthetic_state_dict
+    with torch.device("meta"):
+        model = create_network(args)
+    if args.synthetic_init is not None:
+        sd = synthetic_state_dict(model, args.synthetic_init)
+    else:
+        path = "./saved_info/latent_flow/{}/{}/model_{}.pth".format(args.dataset, args.exp, args.epoch_id)
+        ckpt = torch.load(path, map_location="cpu")
+        for key in list(ckpt.keys()):            # test_flow_latent.py:140-141 (strip "module.")
+            ckpt[key[7:]] = ckpt.pop(key)
+        sd = ckpt
+    model = model.to_empty(device="cpu")
+    model.load_state_dict(sd, strict=True)
+    return model.to(device).eval()
+
+
+def load_vae(args, device):
+    if args.no_decode:
+        return None
+    try:
+        from diffusers.models import AutoencoderKL
+    except ImportError:
+        print("diffusers is not installed: skipping the VAE decode, saving latents instead (--no_decode)")
+        args.no_decode = True
+        return None
+    return AutoencoderKL.from_pretrained(args.pretrained_autoencoder_ckpt).to(device)
+
+
+def make_run_sampling(args, model, vae, device):
+    """test_flow_latent.py:161-194 / test_flow_latent_ddp.py:83-111."""
+    from .solvers import sample_from_model, sample_from_model_with_fixed_step_solver
+
+    def run_sampling(num_samples, generator, cls_index=None, return_nfe=False):
+        side = args.image_size // 8
+        x = generator.randn(num_samples, 4, side, side).to(device)
+        if args.num_classes in [None, 1]:
+            model_kwargs = {}
+        else:
+            if cls_index is None:
+                y = generator.randint(0, args.num_classes, (num_samples,), device=device)
+            else:
+                y = torch.full((num_samples,), cls_index, device=device, dtype=torch.long)
+            if args.cfg_scale > 1.0:
+                x = torch.cat([x, x], 0)
+                y_null = (torch.full((num_samples,), args.num_classes, device=device, dtype=torch.long)
+                          if "DiT" in args.model_type else torch.zeros_like(y))
+                model_kwargs = dict(y=torch.cat([y, y_null], 0), cfg_scale=args.cfg_scale)
+            else:
+                model_kwargs = dict(y=y)
+        nfe = None
+        if not args.use_karras_samplers:
+            out = sample_from_model(model, x, model_kwargs, args)
+            if args.compute_nfe:
+                out, nfe = out
+            fake_sample = out[-1]
+        else:
+            fake_sample = sample_from_model_with_fixed_step_solver(model, x, model_kwargs, generator, args)
+            nfe = model.last_stats["nfe"]
+        if args.cfg_scale > 1.0:
+            fake_sample, _ = fake_sample.chunk(2, dim=0)
+        if vae is None:
+            result = fake_sample
+        else:
+            result = vae.decode(fake_sample / args.scale_factor).sample
+        return (result, nfe) if return_nfe else result
+
+    return run_sampling
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    from . import dist as ldist
+    from .random_util import get_generator
+
+    rank, world, local = ldist.init_from_env()
+    args.world_size = world
+    torch.set_grad_enabled(False)
+    seed = ldist.rank_seed(args.seed, rank)
+    torch.manual_seed(seed)
+    device = torch.device(args.device if args.device else f"cuda:{local}")
+    if device.type == "cuda":
+        torch.cuda.set_device(device)
+        torch.cuda.manual_seed_all(seed)
+    model = load_model(args, device)
+    vae = load_vae(args, device)
+    if rank == 0:
+        print("Finish loading model; parameters: %.2f M" % (sum(p.numel() for p in model.parameters()) / 1e6))
+    generator = get_generator(args.generator, args.n_sample, seed)
+    run_sampling = make_run_sampling(args, model, vae, device)
+    save_dir = os.path.join(args.out_dir, "generated_samples", args.dataset,
+                            "exp{}_ep{}_m{}".format(args.exp, args.epoch_id, args.method))
+    if args.use_karras_samplers or args.method in ("euler", "rk4", "midpoint", "stochastic"):
+        save_dir += "_s{}".format(args.num_steps)
+
+    if args.compute_nfe:
+        was = args.compute_nfe
+        total, trials = 0.0, min(300, args.measure_reps)
+        for _ in range(trials):
+            _, nfe = run_sampling(1, generator, return_nfe=True)
+            total += float(nfe) / trials
+        args.compute_nfe = was
+        print(f"Average NFE over {trials} trials: {int(total)}")
+        return 0
+
+    if args.measure_time:
+        side = args.image_size // 8
+        x = generator.randn(1, 4, side, side).to(device)
+        for _ in range(10):
+            model(torch.tensor(1.0, device=device), x)
+        timings = []
+        for _ in range(args.measure_reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            run_sampling(1, generator)
+            e.record()
+            torch.cuda.synchronize()
+            timings.append(s.elapsed_time(e))
+        print("Inference time: {:.2f}+/-{:.2f}ms".format(float(np.mean(timings)), float(np.std(timings))))
+        return 0
+
+    if args.compute_fid:
+        n = args.batch_size
+        total_samples = ldist.total_samples(args.n_sample, n, world)
+        iters = total_samples // world // n
+        if rank == 0:
+            os.makedirs(save_dir, exist_ok=True)
+            print(f"Total number of images that will be sampled: {total_samples}")
+        if world > 1:
+            torch.distributed.barrier()
+        total = 0
+        for i in range(iters):
+            out = run_sampling(n, generator)
+            if vae is None:
+                for j, z in enumerate(out):
+                    np.save("{}/{}.npy".format(save_dir, ldist.file_index(j, world, rank, total)), z.cpu().numpy())
+            else:
+                import torchvision
+                img = torch.clamp((out + 1.0) / 2.0, 0, 1)
+                for j, im in enumerate(img):
+                    torchvision.utils.save_image(im, "{}/{}.jpg".format(save_dir, ldist.file_index(j, world, rank, total)))
+            total += n * world
+            if rank == 0:
+                print("generating batch ", i)
+        if world > 1:
+            torch.distributed.barrier()
+        if rank == 0:
+            print("samples written to", save_dir, "- run the reference's pytorch_fid on them for the FID statistic")
+        return 0
+
+    # default: one batch; every rank samples its shard and ONE all-gather assembles the result on all ranks
+    out = run_sampling(args.batch_size, generator)
+    out = ldist.all_gather_batch(out)
+    if rank == 0:
+        if args.use_karras_samplers:
+            stem = "samples_{}_{}_{}".format(args.dataset, args.method, args.num_steps)
+        else:
+            stem = "samples_{}_{}_{}_{}".format(args.dataset, args.method, args.atol, args.rtol)
+        if args.num_classes is not None and args.num_classes > 1:
+            stem += "_cfg{}".format(args.cfg_scale)
+        os.makedirs(args.out_dir, exist_ok=True)
+        if vae is None:
+            path = os.path.join(args.out_dir, stem + "_latents.npy")
+            np.save(path, out.cpu().numpy())
+        else:
+            import torchvision
+            path = os.path.join(args.out_dir, stem + ".jpg")
+            torchvision.utils.save_image(torch.clamp((out + 1.0) / 2.0, 0, 1), path, padding=0, nrow=8)
+        print("Samples are save at '{}".format(path))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -193,6 +194,20 @@ static cudaError_t launch_ln(cudaStream_t s, const float* x, __nv_bfloat16* y, c
     }
 }
 
+static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, const CUtensorMap& tout, int B, int H, int D) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention2_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const float scale_log2e = 0.125f * 1.4426950408889634f;
+    const int items = B * H;
+    const int grid = items < g_num_sms ? items : g_num_sms;
+    attention2_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
+    return cudaGetLastError();
+}
+
 static inline unsigned blocks_for(size_t n, int threads = 256) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
 // ------------------------------------------------------------------------------------------------
@@ -331,7 +346,7 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     ctx->HW = desc->img_resolution;
     ctx->chw = ctx->C * ctx->HW * ctx->HW;
     ctx->Nmod = (6 * ctx->L + 2) * ctx->D;
-    ctx->attn_variant = env_int("LFM_ATTN_VARIANT", 0);
+    ctx->attn_variant = env_int("LFM_ATTN_VARIANT", 2);
     const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
 
     if (dev_alloc(ctx, &ctx->pos, (size_t)T * D)) return 1;
@@ -503,19 +518,24 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
 
 static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_numel, const float* x, int x_rows,
                           const long long* y, int rows) {
-    const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T, Nmod = ctx->Nmod;
+    const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
     const int M = rows * T;
-    timestep_features_kernel<<<rows, 256, 0, s>>>(t, t_numel, ctx->tfreq, rows);
+    // Conditioning c = t_emb(t) + y_emb(y) and the adaLN tables.  A 0-d t with y = None (every unconditional
+    // preset) gives the same c for every row: compute ONE row and let all samples read it (table stride 0).
+    const bool uniform_c = (t_numel == 1 && y == nullptr);
+    const int crows = uniform_c ? 1 : rows;
+    const int Nmod = uniform_c ? 0 : ctx->Nmod;  // stride between samples in the modulation table
+    timestep_features_kernel<<<crows, 256, 0, s>>>(t, t_numel, ctx->tfreq, crows);
     LAUNCH_OK();
-    skinny_linear_kernel<0><<<(D + 7) / 8, 256, 0, s>>>(ctx->t_w0, ctx->t_b0, ctx->tfreq, rows, D, 256, nullptr, nullptr,
+    skinny_linear_kernel<0><<<(D + 7) / 8, 256, 0, s>>>(ctx->t_w0, ctx->t_b0, ctx->tfreq, crows, D, 256, nullptr, nullptr,
                                                         0, ctx->h1, nullptr);
     LAUNCH_OK();
-    skinny_linear_kernel<1><<<(D + 7) / 8, 256, 0, s>>>(ctx->t_w2, ctx->t_b2, ctx->h1, rows, D, D, ctx->ytable, y,
+    skinny_linear_kernel<1><<<(D + 7) / 8, 256, 0, s>>>(ctx->t_w2, ctx->t_b2, ctx->h1, crows, D, D, ctx->ytable, y,
                                                         ctx->d.table_rows - 1, nullptr, ctx->c_silu);
     LAUNCH_OK();
-    {   // all adaLN modulation vectors of the network in one GEMM: mod[rows, (6L+2) D]
-        GemmEpi ep{ctx->b_mod, ctx->mod, Nmod, nullptr, 0, 1};
-        CUDA_OK(launch_gemm(s, ctx->tm_csilu, ctx->tm_wmod, rows, Nmod, D, EPI_BIAS_F32, ctx->bn_mod, ep));
+    {   // all adaLN modulation vectors of the network in one GEMM: mod[crows, (6L+2) D]
+        GemmEpi ep{ctx->b_mod, ctx->mod, ctx->Nmod, nullptr, 0, 1};
+        CUDA_OK(launch_gemm(s, ctx->tm_csilu, ctx->tm_wmod, crows, ctx->Nmod, D, EPI_BIAS_F32, ctx->bn_mod, ep));
         ctx->launches++;
     }
     patch_embed_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, x_rows, ctx->pe_w, ctx->pe_b, ctx->pos, ctx->x_tok, D, ctx->G,
@@ -531,7 +551,9 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
             CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv));
             ctx->launches++;
         }
-        if (ctx->attn_variant == 0)
+        if (ctx->attn_variant == 2)
+            CUDA_OK(launch_attention2(s, ctx->tm_qkv_kv, ctx->tm_attn, rows, ctx->H, D));
+        else if (ctx->attn_variant == 0)
             CUDA_OK(launch_attention_inst<true>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
         else
             CUDA_OK(launch_attention_inst<false>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
@@ -1008,7 +1030,18 @@ extern "C" int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, in
     if (!make_tmap_bf16(&tq, qkv_bf16, M, 3 * D, 128) || !make_tmap_bf16(&tkv, qkv_bf16, M, 3 * D, 256))
         return fail(ctx, "lfm_dbg_attention: tensor map encode failed");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (variant == 0)
+    if (variant == 2) {
+        if (g_num_sms == 0) {
+            int dev = 0;
+            CUDA_OK(cudaGetDevice(&dev));
+            cudaDeviceProp prop;
+            CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+            g_num_sms = prop.multiProcessorCount;
+        }
+        CUtensorMap tout;
+        if (!make_tmap_bf16(&tout, out_bf16, M, D, 128)) return fail(ctx, "lfm_dbg_attention: tensor map encode failed");
+        CUDA_OK(launch_attention2(s, tkv, tout, B, H, D));
+    } else if (variant == 0)
         CUDA_OK(launch_attention_inst<true>(s, tq, tkv, static_cast<__nv_bfloat16*>(out_bf16), B, H, D, dbg_s));
     else
         CUDA_OK(launch_attention_inst<false>(s, tq, tkv, static_cast<__nv_bfloat16*>(out_bf16), B, H, D, dbg_s));
