@@ -69,6 +69,69 @@ def build(models, kwargs, seed, factory=None):
     return net, cfg
 
 
+UNET_CASES = {
+    # small ADM nets with the celeb512 topology rules (attention at ds 2 and 4 => 16x16 / 8x8 tokens here)
+    "unet_mini": (dict(image_size=32, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+                       attention_resolutions=(2, 4), channel_mult=(1, 2, 2), num_heads=2, num_head_channels=-1,
+                       num_classes=None), 21, 2),
+    "unet_mini_cond": (dict(image_size=32, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=2,
+                            attention_resolutions=(4,), channel_mult=(1, 1, 2), num_heads=4, num_head_channels=-1,
+                            num_classes=7), 22, 2),
+}
+
+
+def make_unet_goldens(g):
+    """ADM UNetModel fixtures from the reference's own module (models/guided_diffusion/unet.py)."""
+    from models.guided_diffusion.unet import UNetModel
+    from oracle import unet as ounet
+
+    for name, (kw, seed, B) in UNET_CASES.items():
+        cfg = ounet.UNetConfig(**kw)
+        net = UNetModel(image_size=kw["image_size"], in_channels=kw["in_channels"], model_channels=kw["model_channels"],
+                        out_channels=kw["out_channels"], num_res_blocks=kw["num_res_blocks"],
+                        attention_resolutions=kw["attention_resolutions"], dropout=0.0, channel_mult=kw["channel_mult"],
+                        conv_resample=True, dims=2, num_classes=kw["num_classes"], use_checkpoint=False, use_fp16=False,
+                        num_heads=kw["num_heads"], num_head_channels=kw["num_head_channels"], num_heads_upsample=-1,
+                        use_scale_shift_norm=True, resblock_updown=False, use_new_attention_order=False)
+        sd = ounet.synthetic_state_dict(cfg, seed)
+        net.load_state_dict(sd, strict=True)   # pins the key set / shapes of oracle.unet.param_shapes
+        net.eval()
+        x = torch.randn(B, 4, kw["image_size"], kw["image_size"], generator=g)
+        tv = torch.tensor([0.85, 0.3][:B])
+        out = {"x": x, "t_vec": tv, "weight_seed": np.int64(seed)}
+        for k, v in kw.items():
+            if v is not None and not isinstance(v, tuple):
+                out["cfg_" + k] = np.float64(v)
+        out["cfg_attention_resolutions"] = np.array(kw["attention_resolutions"], dtype=np.int64)
+        out["cfg_channel_mult"] = np.array(kw["channel_mult"], dtype=np.int64)
+        if kw["num_classes"] is None:
+            out["v"] = net(tv, x)
+        else:
+            y = torch.randint(0, kw["num_classes"], (B,), generator=g)
+            out["y"] = y
+            out["v"] = net(tv, x, y)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
+        print("wrote", name, "absmean(v)=%.4f" % float(out["v"].abs().mean()))
+
+    # the celeb256 preset at full width (test_args/celeb256_adm.txt): B=1
+    kw = dict(image_size=32, in_channels=4, model_channels=256, out_channels=4, num_res_blocks=2,
+              attention_resolutions=(16, 8), channel_mult=(1, 2, 2, 2), num_heads=4, num_head_channels=-1, num_classes=None)
+    cfg = ounet.UNetConfig(**kw)
+    net = UNetModel(image_size=32, in_channels=4, model_channels=256, out_channels=4, num_res_blocks=2,
+                    attention_resolutions=(16, 8), dropout=0.0, channel_mult=(1, 2, 2, 2), conv_resample=True, dims=2,
+                    num_classes=None, use_checkpoint=False, use_fp16=False, num_heads=4, num_head_channels=-1,
+                    num_heads_upsample=-1, use_scale_shift_norm=True, resblock_updown=False, use_new_attention_order=False)
+    sd = ounet.synthetic_state_dict(cfg, 1)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    x = torch.randn(1, 4, 32, 32, generator=g)
+    tv = torch.tensor([0.6])
+    np.savez_compressed(os.path.join(OUT, "unet_celeb256.npz"), x=x.numpy(), t_vec=tv.numpy(), v=net(tv, x).numpy(),
+                        weight_seed=np.int64(1), n_tensors=np.int64(len(sd)))
+    print("wrote unet_celeb256", len(sd), "tensors")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
@@ -133,6 +196,8 @@ def main():
                             **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
         print("wrote", name)
         del net
+
+    make_unet_goldens(torch.Generator().manual_seed(4321))
 
     # spot values of the fixed table quoted in SURVEY.md 8(c)
     pe = odit.pos_embed_2d(1024, 16)
