@@ -25,7 +25,7 @@ extern "C" {
 
 typedef struct lfm_ctx lfm_ctx;
 
-enum { LFM_ARCH_DIT = 0 };
+enum { LFM_ARCH_DIT = 0, LFM_ARCH_UNET = 1 };
 enum { LFM_DTYPE_F32 = 0 };
 enum { LFM_METHOD_EULER = 0, LFM_METHOD_HEUN = 1 };
 
@@ -43,6 +43,24 @@ typedef struct lfm_model_desc {
     int32_t table_rows;      /* y_embedder rows = num_classes + (label_dropout > 0) (models/DiT.py:79-81) */
 } lfm_model_desc;
 
+/* Constructor arguments of the reference ADM network (models/guided_diffusion/unet.py:407-428 as called by
+ * get_flow_model, models/__init__.py:46-68).  Only the configuration the LFM presets use is implemented:
+ * use_scale_shift_norm = True, resblock_updown = False, conv_resample = True, legacy attention order, dims = 2. */
+typedef struct lfm_unet_desc {
+    int32_t image_size;                /* latent side (config.image_size // 8), e.g. 64 */
+    int32_t in_channels;               /* 4 */
+    int32_t model_channels;            /* nf, multiple of 128 */
+    int32_t out_channels;              /* 4 */
+    int32_t num_res_blocks;
+    int32_t n_attn_res;                /* number of entries used in attention_resolutions */
+    int32_t attention_resolutions[8];  /* DOWNSAMPLE RATES at which attention is applied (unet.py:482) */
+    int32_t n_mult;                    /* number of entries used in channel_mult */
+    int32_t channel_mult[8];
+    int32_t num_heads;
+    int32_t num_head_channels;         /* -1: use num_heads */
+    int32_t num_classes;               /* 0: unconditional; > 0: label_emb rows (y is then required) */
+} lfm_unet_desc;
+
 typedef struct lfm_ode_stats {
     int64_t nfe;       /* network evaluations */
     int64_t accepted;  /* dopri5 accepted steps */
@@ -51,6 +69,11 @@ typedef struct lfm_ode_stats {
 
 /* models/__init__.py:6-17 create_network(config) -> nn.Module.  Creates an empty context on `device`. */
 int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out);
+
+/* models/__init__.py:20-70 get_flow_model(config) -> UNetModel (config.use_origin_adm).  The same
+ * lfm_set_param / lfm_finalize / lfm_forward / lfm_sample_* entry points then operate on the UNet
+ * (model(t, x, y) = UNetModel.forward, unet.py:613-655; it has no forward_with_cfg: cfg_scale must be <= 1). */
+int lfm_create_unet(const lfm_unet_desc* desc, int device, lfm_ctx** out);
 
 /* nn.Module.load_state_dict (test_flow_latent.py:142): one call per state-dict entry, `key` exactly as in the
  * reference state_dict; `ptr` may be a host or a device pointer (fp32).  The data is copied

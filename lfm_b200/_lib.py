@@ -14,6 +14,13 @@ class ModelDesc(C.Structure):
                 ("num_heads", C.c_int32), ("mlp_hidden", C.c_int32), ("table_rows", C.c_int32)]
 
 
+class UnetDesc(C.Structure):
+    _fields_ = [("image_size", C.c_int32), ("in_channels", C.c_int32), ("model_channels", C.c_int32),
+                ("out_channels", C.c_int32), ("num_res_blocks", C.c_int32), ("n_attn_res", C.c_int32),
+                ("attention_resolutions", C.c_int32 * 8), ("n_mult", C.c_int32), ("channel_mult", C.c_int32 * 8),
+                ("num_heads", C.c_int32), ("num_head_channels", C.c_int32), ("num_classes", C.c_int32)]
+
+
 class OdeStats(C.Structure):
     _fields_ = [("nfe", C.c_int64), ("accepted", C.c_int64), ("rejected", C.c_int64)]
 
@@ -22,6 +29,7 @@ class OdeStats(C.Structure):
 _P = C.c_void_p
 SYMBOLS = {
     "lfm_create": (C.c_int, [C.POINTER(ModelDesc), C.c_int, C.POINTER(_P)]),
+    "lfm_create_unet": (C.c_int, [C.POINTER(UnetDesc), C.c_int, C.POINTER(_P)]),
     "lfm_set_param": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "lfm_finalize": (C.c_int, [_P, C.c_int]),
     "lfm_forward": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_float, _P, _P]),

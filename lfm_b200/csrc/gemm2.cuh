@@ -52,6 +52,28 @@ LFM_DEVICE void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* 
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1)
         : "memory");
 }
+// 4-D variant (NHWC activation tensor {C, W, H, B}): the im2col gather of one filter tap is a shifted box;
+// out-of-bounds rows/columns (the zero padding) are zero-filled by TMA.
+LFM_DEVICE void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2,
+                                int32_t c3) {
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// Implicit-GEMM convolution geometry (taps == 0: plain GEMM, A is a 2-D [M, K] matrix).
+// Output pixels are flattened (b, h, w) row-major; a CTA's 128 output rows are whole image rows (W * rows == 128)
+// or whole images (H * W divides 128), so the matching input window of tap (r, s) is ONE 4-D box.
+struct ConvGeom {
+    int taps;     // 0 (GEMM), 9 (3x3, pad 1)
+    int cblocks;  // C_in / 64
+    int W;        // OUTPUT width
+    int HW;       // OUTPUT height * width
+    int stride;   // 1 or 2 (the tensor map carries the matching element strides)
+};
+
 LFM_DEVICE void umma_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -151,7 +173,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], box {64, 128}
                    const __grid_constant__ CUtensorMap tmap_b,   // W [N, K], box {64, 128}
                    const __grid_constant__ CUtensorMap tmap_out, // out [M, ldo]: box {128 bytes, 32 rows}, 128B swizzle
-                   int M, int N, int K, GemmEpi ep) {
+                   int M, int N, int K, GemmEpi ep, ConvGeom cg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -207,10 +229,26 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
                 const int row_a = m_blk * 256 + static_cast<int>(rank) * 128;
                 const int row_b = n_blk * kG2BlockN + static_cast<int>(rank) * 128;
+                int img0 = 0, h0 = 0;
+                if (cg.taps != 0) {
+                    img0 = row_a / cg.HW;
+                    h0 = (row_a % cg.HW) / cg.W;
+                }
+                int tap = 0, cb = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kG2StageBytes);
-                    tma_load_2d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * 64, row_a);
+                    if (cg.taps == 0) {
+                        tma_load_2d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * 64, row_a);
+                    } else {
+                        const int r = tap / 3, sx = tap - 3 * r;
+                        tma_load_4d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], cb * 64, sx - 1,
+                                        cg.stride * h0 + r - 1, img0);
+                        if (++cb == cg.cblocks) {
+                            cb = 0;
+                            ++tap;
+                        }
+                    }
                     tma_load_2d_2sm(smem_b + stage * kG2BBytes, &tmap_b, &full_bar[stage], kb * 64, row_b);
                     if (++stage == kG2Stages) {
                         stage = 0;
@@ -267,7 +305,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
             const int row = row0 + lane;
             const int nbase = n_blk * kG2BlockN + half * 128;
             const float* gate_row = nullptr;
-            if (EPI == EPI_GATE_RESID_F32)
+            if (EPI == EPI_GATE_RESID_F32 && ep.gate != nullptr)  // gate == nullptr: plain residual add (gate 1)
                 gate_row = ep.gate + static_cast<size_t>((row < M ? row : M - 1) / ep.rows_per_sample) * ep.gate_stride;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();

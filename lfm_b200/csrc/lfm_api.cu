@@ -2,6 +2,7 @@
 // Single translation unit; build:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared ...
 #include "../../include/lfm_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -17,6 +18,7 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "kernels.cuh"
+#include "unet.cuh"
 
 using namespace lfm;
 
@@ -107,7 +109,8 @@ static cudaError_t launch_gemm_inst(cudaStream_t s, const CUtensorMap& ta, const
 // 2-CTA pair kernel (256 x 256 tile per cluster of two CTAs)
 template <int EPI>
 static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb,
-                                     const CUtensorMap& tout, int M, int N, int K, const GemmEpi& ep) {
+                                     const CUtensorMap& tout, int M, int N, int K, const GemmEpi& ep,
+                                     ConvGeom cg = ConvGeom{0, 0, 0, 0, 1}) {
     static bool attr_set = false;
     auto kern = gemm2_bf16_tcgen05<EPI>;
     if (!attr_set) {
@@ -118,7 +121,7 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
     const int tiles = ((M + 255) / 256) * ((N + kG2BlockN - 1) / kG2BlockN);
     int clusters = g_num_sms / 2;
     if (tiles < clusters) clusters = tiles;
-    kern<<<2 * clusters, kG2Threads, kG2SmemBytes, s>>>(ta, tb, tout, M, N, K, ep);
+    kern<<<2 * clusters, kG2Threads, kG2SmemBytes, s>>>(ta, tb, tout, M, N, K, ep, cg);
     return cudaGetLastError();
 }
 
@@ -218,6 +221,7 @@ struct ParamSlot {
     std::vector<int64_t> shape;
     size_t numel = 0;
     bool to_bf16 = false;
+    int kind = 0;  // 0 copy fp32, 1 cast bf16, 2 conv [Co,Ci,kh,kw] -> bf16 [Co,kh,kw,Ci], 3 out-conv -> fp32 [4][9][C]
     bool set = false;
 };
 
@@ -227,8 +231,12 @@ struct BlockW {
     CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
 };
 
+struct UNetState;
+
 struct lfm_ctx {
     lfm_model_desc d{};
+    int arch = LFM_ARCH_DIT;
+    UNetState* un = nullptr;
     int device = 0;
     int D = 0, L = 0, H = 0, T = 0, G = 0, C = 0, Hd = 0, Nmod = 0, HW = 0, chw = 0;
     int max_rows = 0;
@@ -268,6 +276,7 @@ struct lfm_ctx {
     float* ratio_host = nullptr;  // pinned
     struct StepGraph {
         cudaGraphExec_t exec = nullptr;
+        int launches = 0;  // kernels per replay (measured on the warm-up run)
     };
     std::map<std::string, StepGraph> graphs;
 };
@@ -300,7 +309,12 @@ static void add_param(lfm_ctx* ctx, const std::string& key, void* dst, std::vect
     s.numel = 1;
     for (int64_t v : shape) s.numel *= static_cast<size_t>(v);
     s.to_bf16 = to_bf16;
+    s.kind = to_bf16 ? 1 : 0;
     ctx->params[key] = s;
+}
+static void add_param_kind(lfm_ctx* ctx, const std::string& key, void* dst, std::vector<int64_t> shape, int kind) {
+    add_param(ctx, key, dst, shape, kind != 0);
+    ctx->params[key].kind = kind;
 }
 
 static int env_int(const char* name, int dflt) {
@@ -424,7 +438,16 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
             ctx->staging_elems = s.numel;
         }
         CUDA_OK(cudaMemcpy(ctx->staging, ptr, s.numel * sizeof(float), cudaMemcpyDefault));
-        f32_to_bf16_kernel<<<blocks_for((s.numel + 3) / 4), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst), s.numel);
+        if (s.kind == 2) {
+            const int taps = static_cast<int>(s.shape[2] * s.shape[3]);
+            conv_weight_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst),
+                                                                   static_cast<int>(s.shape[0]), static_cast<int>(s.shape[1]), taps);
+        } else if (s.kind == 3) {
+            conv_out_weight_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<float*>(s.dst),
+                                                                       static_cast<int>(s.shape[1]));
+        } else {
+            f32_to_bf16_kernel<<<blocks_for((s.numel + 3) / 4), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst), s.numel);
+        }
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaDeviceSynchronize());
     }
@@ -439,27 +462,7 @@ static int pick_bn(int N, const char* env, int dflt) {
     return bn;
 }
 
-extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
-    if (ctx == nullptr) return fail(ctx, "lfm_finalize: null ctx");
-    if (max_batch < 1) return fail(ctx, "lfm_finalize: max_batch must be >= 1");
-    for (auto& kv : ctx->params)
-        if (!kv.second.set) return fail(ctx, "lfm_finalize: missing key '%s' (strict)", kv.first.c_str());
-    if (ctx->finalized && max_batch <= ctx->max_rows) return 0;
-    if (ctx->finalized) return fail(ctx, "lfm_finalize: already finalized for %d rows; create a new ctx for %d", ctx->max_rows, max_batch);
-    CUDA_OK(cudaSetDevice(ctx->device));
-    const int D = ctx->D, Hd = ctx->Hd, T = ctx->T, R = max_batch;
-    const size_t M = (size_t)R * T;
-    const int Rpad = R < 128 ? 128 : R;
-    if (dev_alloc(ctx, &ctx->x_tok, M * D)) return 1;
-    if (dev_alloc(ctx, &ctx->xn, M * D)) return 1;
-    if (dev_alloc(ctx, &ctx->qkv, M * 3 * D)) return 1;
-    if (dev_alloc(ctx, &ctx->attn, M * D)) return 1;
-    if (dev_alloc(ctx, &ctx->hmid, M * Hd)) return 1;
-    if (dev_alloc(ctx, &ctx->mod, (size_t)R * ctx->Nmod)) return 1;
-    if (dev_alloc(ctx, &ctx->c_silu, (size_t)Rpad * D)) return 1;
-    if (dev_alloc(ctx, &ctx->tfreq, (size_t)R * 256)) return 1;
-    if (dev_alloc(ctx, &ctx->h1, (size_t)R * D)) return 1;
-    if (dev_alloc(ctx, &ctx->v_net, (size_t)R * ctx->chw)) return 1;
+static int alloc_solver_state(lfm_ctx* ctx, int R) {
     // solver state (sized for R latent rows)
     const size_t nst = (size_t)R * ctx->chw;
     if (dev_alloc(ctx, &ctx->x_state, nst)) return 1;
@@ -477,6 +480,40 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
     if (dev_alloc(ctx, &ctx->y_buf, (size_t)R)) return 1;
     if (dev_alloc(ctx, &ctx->step_state, 1)) return 1;
     CUDA_OK(cudaMallocHost(&ctx->ratio_host, 64));
+    return 0;
+}
+
+static int unet_finalize(lfm_ctx* ctx, int R);
+
+extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
+    if (ctx == nullptr) return fail(ctx, "lfm_finalize: null ctx");
+    if (max_batch < 1) return fail(ctx, "lfm_finalize: max_batch must be >= 1");
+    for (auto& kv : ctx->params)
+        if (!kv.second.set) return fail(ctx, "lfm_finalize: missing key '%s' (strict)", kv.first.c_str());
+    if (ctx->finalized && max_batch <= ctx->max_rows) return 0;
+    if (ctx->finalized) return fail(ctx, "lfm_finalize: already finalized for %d rows; create a new ctx for %d", ctx->max_rows, max_batch);
+    CUDA_OK(cudaSetDevice(ctx->device));
+    if (ctx->arch == LFM_ARCH_UNET) {
+        if (unet_finalize(ctx, max_batch)) return 1;
+        if (alloc_solver_state(ctx, max_batch)) return 1;
+        ctx->max_rows = max_batch;
+        ctx->finalized = true;
+        return 0;
+    }
+    const int D = ctx->D, Hd = ctx->Hd, T = ctx->T, R = max_batch;
+    const size_t M = (size_t)R * T;
+    const int Rpad = R < 128 ? 128 : R;
+    if (dev_alloc(ctx, &ctx->x_tok, M * D)) return 1;
+    if (dev_alloc(ctx, &ctx->xn, M * D)) return 1;
+    if (dev_alloc(ctx, &ctx->qkv, M * 3 * D)) return 1;
+    if (dev_alloc(ctx, &ctx->attn, M * D)) return 1;
+    if (dev_alloc(ctx, &ctx->hmid, M * Hd)) return 1;
+    if (dev_alloc(ctx, &ctx->mod, (size_t)R * ctx->Nmod)) return 1;
+    if (dev_alloc(ctx, &ctx->c_silu, (size_t)Rpad * D)) return 1;
+    if (dev_alloc(ctx, &ctx->tfreq, (size_t)R * 256)) return 1;
+    if (dev_alloc(ctx, &ctx->h1, (size_t)R * D)) return 1;
+    if (dev_alloc(ctx, &ctx->v_net, (size_t)R * ctx->chw)) return 1;
+    if (alloc_solver_state(ctx, R)) return 1;
 
     // default: the CTA-pair kernel for every token-level GEMM (LFM_BN_* = 128 / 256 selects the 1-CTA kernel)
     ctx->bn_qkv = pick_bn(3 * D, "LFM_BN_QKV", kGemmPair);
@@ -516,8 +553,11 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
         ctx->launches++;                              \
     } while (0)
 
+#include "unet_host.inc"
+
 static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_numel, const float* x, int x_rows,
                           const long long* y, int rows) {
+    if (ctx->arch == LFM_ARCH_UNET) return launch_unet(ctx, s, t, t_numel, x, x_rows, y, rows);
     const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
     const int M = rows * T;
     // Conditioning c = t_emb(t) + y_emb(y) and the adaLN tables.  A 0-d t with y = None (every unconditional
@@ -599,6 +639,8 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
 static int eval_velocity(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_numel, const float* x, int n_img,
                          const long long* y, float cfg_scale, float* v_out) {
     const size_t n = (size_t)n_img * ctx->chw;
+    if (cfg_scale > 1.0f && ctx->arch == LFM_ARCH_UNET)
+        return fail(ctx, "UNetModel has no forward_with_cfg (reference models/guided_diffusion/unet.py): cfg_scale must be <= 1");
     if (cfg_scale > 1.0f) {
         if (launch_network(ctx, s, t, t_numel, x, n_img, y, 2 * n_img)) return 1;
         cfg_combine_kernel<<<blocks_for(n), 256, 0, s>>>(ctx->v_net, v_out, n, cfg_scale, 0);
@@ -626,6 +668,8 @@ extern "C" int lfm_forward(lfm_ctx* ctx, const float* t, int t_numel, const floa
     CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long* yl = reinterpret_cast<const long long*>(y);
+    if (cfg_scale > 1.0f && ctx->arch == LFM_ARCH_UNET)
+        return fail(ctx, "lfm_forward: UNetModel has no forward_with_cfg; cfg_scale must be <= 1");
     if (cfg_scale > 1.0f) {
         if (B % 2 != 0) return fail(ctx, "lfm_forward: forward_with_cfg needs an even batch (got %d)", B);
         if (t_numel != 1) {
@@ -684,12 +728,14 @@ static int record_step(lfm_ctx* ctx, int kind /*0 euler, 1 heun (with corrector)
     return 0;
 }
 
-static int get_step_graph(lfm_ctx* ctx, int kind, int n_img, bool has_y, float cfg_scale, cudaGraphExec_t* out) {
+static int get_step_graph(lfm_ctx* ctx, int kind, int n_img, bool has_y, float cfg_scale, cudaGraphExec_t* out,
+                          int* launches) {
     char key[128];
     snprintf(key, sizeof(key), "k%d_n%d_y%d_c%.6f", kind, n_img, has_y ? 1 : 0, cfg_scale > 1.0f ? cfg_scale : 0.f);
     auto it = ctx->graphs.find(key);
     if (it != ctx->graphs.end()) {
         *out = it->second.exec;
+        *launches = it->second.launches;
         return 0;
     }
     if (env_int("LFM_NO_GRAPH", 0)) {
@@ -700,6 +746,7 @@ static int get_step_graph(lfm_ctx* ctx, int kind, int n_img, bool has_y, float c
     const int64_t launches_before = ctx->launches;
     if (record_step(ctx, kind, n_img, has_y, cfg_scale)) return 1;
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    const int launches_per_replay = static_cast<int>(ctx->launches - launches_before);
     StepState zero{0, 0};
     // (the warm-up advanced the device step counter and state; callers re-initialise both afterwards)
     cudaGraph_t graph = nullptr;
@@ -714,14 +761,10 @@ static int get_step_graph(lfm_ctx* ctx, int kind, int n_img, bool has_y, float c
     CUDA_OK(cudaGraphDestroy(graph));
     (void)zero;
     ctx->graphs[key].exec = exec;
+    ctx->graphs[key].launches = launches_per_replay;
+    *launches = launches_per_replay;
     *out = exec;
     return 0;
-}
-
-static int launches_per_step(lfm_ctx* ctx, int kind, float cfg_scale) {
-    const int net = 5 + 7 * ctx->L + 1;
-    const int ev = net + (cfg_scale > 1.0f ? 1 : 0);  // (+ a d2d memcpy node when no CFG; not a kernel)
-    return kind == 0 ? (1 + ev + 1 + 1) : (1 + ev + 1 + 1 + ev + 1 + 1);
 }
 
 extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const float* t_grid_host, int n_grid,
@@ -745,9 +788,10 @@ extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const 
     const int n_heun = method == LFM_METHOD_HEUN ? (heun_corrector_limit < n_int ? (heun_corrector_limit < 0 ? 0 : heun_corrector_limit) : n_int) : 0;
     const bool graphs = !env_int("LFM_NO_GRAPH", 0);
     if (join_in(ctx, user)) return 1;
+    int l_euler = 0, l_heun = 0;
     if (graphs) {
-        if (n_heun < n_int && get_step_graph(ctx, 0, B_img, has_y, cfg_scale, &g_euler)) return 1;
-        if (n_heun > 0 && get_step_graph(ctx, 1, B_img, has_y, cfg_scale, &g_heun)) return 1;
+        if (n_heun < n_int && get_step_graph(ctx, 0, B_img, has_y, cfg_scale, &g_euler, &l_euler)) return 1;
+        if (n_heun > 0 && get_step_graph(ctx, 1, B_img, has_y, cfg_scale, &g_heun, &l_heun)) return 1;
     }
     cudaStream_t s = ctx->stream;
     CUDA_OK(cudaMemcpyAsync(ctx->t_grid, t_grid_host, (size_t)n_grid * sizeof(float), cudaMemcpyDefault, s));
@@ -762,7 +806,7 @@ extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const 
         cudaGraphExec_t g = kind ? g_heun : g_euler;
         if (g != nullptr) {
             CUDA_OK(cudaGraphLaunch(g, s));
-            ctx->launches += launches_per_step(ctx, kind, cfg_scale);
+            ctx->launches += kind ? l_heun : l_euler;
         } else {
             if (record_step(ctx, kind, B_img, has_y, cfg_scale)) return 1;
         }
@@ -987,6 +1031,7 @@ extern "C" void lfm_destroy(lfm_ctx* ctx) {
         if (g.second.exec != nullptr) cudaGraphExecDestroy(g.second.exec);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->staging != nullptr) cudaFree(ctx->staging);
+    delete ctx->un;
     if (ctx->ratio_host != nullptr) cudaFreeHost(ctx->ratio_host);
     if (ctx->stream != nullptr) cudaStreamDestroy(ctx->stream);
     if (ctx->ev_in != nullptr) cudaEventDestroy(ctx->ev_in);
@@ -1050,6 +1095,7 @@ extern "C" int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, in
 
 extern "C" int lfm_dbg_tokens(lfm_ctx* ctx, float* out, int B) {
     if (check_ready(ctx, B, "lfm_dbg_tokens")) return 1;
+    if (ctx->arch != LFM_ARCH_DIT) return fail(ctx, "lfm_dbg_tokens: DiT only");
     CUDA_OK(cudaMemcpy(out, ctx->x_tok, (size_t)B * ctx->T * ctx->D * sizeof(float), cudaMemcpyDefault));
     return 0;
 }

@@ -1,0 +1,354 @@
+// lfm_b200 - non-GEMM kernels of the ADM UNetModel velocity network (reference models/guided_diffusion/unet.py).
+// Activations are NHWC: an fp32 "stream" tensor per block output (skip connections, residual adds) and bf16 operand
+// tensors feeding the tcgen05 implicit-GEMM convolutions (gemm2.cuh with a 4-D TMA im2col producer).
+#pragma once
+#include "common.cuh"
+
+namespace lfm {
+
+// Channel-concatenated view of up to two NHWC fp32 tensors (th.cat([h, hs.pop()], dim=1), unet.py:649 - the
+// concatenation is never materialised: GroupNorm reads both sources and writes ONE bf16 operand).
+struct Src2 {
+    const float* a;
+    const float* b;  // may be nullptr
+    int Ca, Cb;
+};
+
+LFM_DEVICE float4 src2_load(const Src2& s, size_t pix, int ch) {
+    if (ch < s.Ca) return *reinterpret_cast<const float4*>(s.a + pix * s.Ca + ch);
+    return *reinterpret_cast<const float4*>(s.b + pix * s.Cb + (ch - s.Ca));
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm32(32, C) statistics (nn.py:17-19; eps 1e-5, biased variance over (C/32) x H x W per sample).
+// grid (nchunk, B): each block reduces a pixel range of one sample into 32 x {sum, sumsq} (fp64 bins),
+// partial[b][chunk][32][2].  One warp per pixel; lane l owns channels 128 j + 4 l .. + 3 (C % 128 == 0, so a
+// float4 never straddles a group).
+constexpr int kGnMaxJ = 24;  // C <= 3072
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(Src2 s, int HW, int C, int nchunk, double* __restrict__ partial) {
+    __shared__ double bins[32][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    const int J = C / 128, cpg = C / 32;
+    if (threadIdx.x < 64) bins[threadIdx.x >> 1][threadIdx.x & 1] = 0.0;
+    __syncthreads();
+    const int p0 = static_cast<int>(static_cast<long long>(HW) * chunk / nchunk);
+    const int p1 = static_cast<int>(static_cast<long long>(HW) * (chunk + 1) / nchunk);
+    float sum[kGnMaxJ], sq[kGnMaxJ];
+#pragma unroll
+    for (int j = 0; j < kGnMaxJ; ++j) sum[j] = sq[j] = 0.f;
+    for (int p = p0 + warp; p < p1; p += 8) {
+        const size_t pix = static_cast<size_t>(b) * HW + p;
+#pragma unroll
+        for (int j = 0; j < kGnMaxJ; ++j) {
+            if (j < J) {
+                const float4 v = src2_load(s, pix, 128 * j + 4 * lane);
+                sum[j] += (v.x + v.y) + (v.z + v.w);
+                sq[j] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kGnMaxJ; ++j) {
+        if (j < J) {
+            const int g = (128 * j + 4 * lane) / cpg;
+            atomicAdd(&bins[g][0], static_cast<double>(sum[j]));
+            atomicAdd(&bins[g][1], static_cast<double>(sq[j]));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64)
+        partial[(static_cast<size_t>(b) * nchunk + chunk) * 64 + threadIdx.x] = bins[threadIdx.x >> 1][threadIdx.x & 1];
+}
+
+// GroupNorm apply (+ optional FiLM h*(1+scale)+shift, unet.py:230-234; + optional SiLU) -> bf16 operand.
+// Also (optionally) copies the fp32 input through (pre-initialises the ResBlock output for the identity skip,
+// unet.py:238 `skip_connection(x) + h`) and/or writes a raw bf16 cast (operand of the 1x1 skip convolution).
+struct GnApplyArgs {
+    Src2 src;
+    int HW, C, nchunk;
+    const double* partial;
+    const float* gamma;
+    const float* beta;
+    const float* film;  // nullptr, or per-sample [scale(C) | shift(C)] at film + b * film_stride
+    int film_stride;
+    int act;            // 0 none, 1 SiLU
+    __nv_bfloat16* out;
+    float* copy_out;            // nullptr or fp32 [B, HW, C]
+    __nv_bfloat16* raw_out;     // nullptr or bf16 [B, HW, C]
+};
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(GnApplyArgs a) {
+    __shared__ float s_mean[32], s_rstd[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int J = a.C / 128, cpg = a.C / 32;
+    if (threadIdx.x < 32) {
+        double S = 0.0, Q = 0.0;
+        for (int c = 0; c < a.nchunk; ++c) {  // fixed order => deterministic
+            S += a.partial[(static_cast<size_t>(b) * a.nchunk + c) * 64 + 2 * threadIdx.x];
+            Q += a.partial[(static_cast<size_t>(b) * a.nchunk + c) * 64 + 2 * threadIdx.x + 1];
+        }
+        const double n = static_cast<double>(a.HW) * cpg;
+        const double mean = S / n;
+        double var = Q / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = static_cast<float>(mean);
+        s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+    }
+    __syncthreads();
+    const float* film = a.film != nullptr ? a.film + static_cast<size_t>(b) * a.film_stride : nullptr;
+    for (int p = blockIdx.x * 8 + warp; p < a.HW; p += gridDim.x * 8) {
+        const size_t pix = static_cast<size_t>(b) * a.HW + p;
+        for (int j = 0; j < J; ++j) {
+            const int ch = 128 * j + 4 * lane;
+            const float4 v = src2_load(a.src, pix, ch);
+            const int g = ch / cpg;
+            const float mean = s_mean[g], rstd = s_rstd[g];
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(a.gamma + ch));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta + ch));
+            float y0 = fmaf((v.x - mean) * rstd, ga.x, be.x);
+            float y1 = fmaf((v.y - mean) * rstd, ga.y, be.y);
+            float y2 = fmaf((v.z - mean) * rstd, ga.z, be.z);
+            float y3 = fmaf((v.w - mean) * rstd, ga.w, be.w);
+            if (film != nullptr) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(film + ch));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(film + a.C + ch));
+                y0 = fmaf(y0, 1.f + sc.x, sh.x);
+                y1 = fmaf(y1, 1.f + sc.y, sh.y);
+                y2 = fmaf(y2, 1.f + sc.z, sh.z);
+                y3 = fmaf(y3, 1.f + sc.w, sh.w);
+            }
+            if (a.act) {
+                y0 = silu(y0), y1 = silu(y1), y2 = silu(y2), y3 = silu(y3);
+            }
+            *reinterpret_cast<uint2*>(a.out + pix * a.C + ch) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+            if (a.copy_out != nullptr) *reinterpret_cast<float4*>(a.copy_out + pix * a.C + ch) = v;
+            if (a.raw_out != nullptr)
+                *reinterpret_cast<uint2*>(a.raw_out + pix * a.C + ch) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// input_blocks.0: conv3x3(in_channels=4 -> C), pad 1, NCHW fp32 latents -> NHWC fp32 stream (unet.py:464).
+// Network row b reads sample b % x_rows.  One block per output row (b, h); thread = output channel.
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float* __restrict__ x, int x_rows, const float* __restrict__ Wt /*[C,4,3,3]*/,
+               const float* __restrict__ bias, float* __restrict__ out, int H, int W, int C) {
+    extern __shared__ float s_in[];  // [4][3][W + 2]
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int bs = b % x_rows;
+    const int WP = W + 2;
+    for (int i = threadIdx.x; i < 4 * 3 * WP; i += blockDim.x) {
+        const int c = i / (3 * WP), r = (i / WP) % 3, w = i % WP - 1;
+        const int hh = h + r - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && w >= 0 && w < W) v = x[((static_cast<size_t>(bs) * 4 + c) * H + hh) * W + w];
+        s_in[i] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float wreg[36];
+#pragma unroll
+        for (int i = 0; i < 36; ++i) wreg[i] = __ldg(Wt + static_cast<size_t>(c) * 36 + i);
+        const float bc = bias[c];
+        for (int w = 0; w < W; ++w) {
+            float acc = bc;
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) acc = fmaf(wreg[ci * 9 + r * 3 + s], s_in[(ci * 3 + r) * WP + w + s], acc);
+            out[((static_cast<size_t>(b) * H + h) * W + w) * C + c] = acc;
+        }
+    }
+}
+
+// out.2: conv3x3(C -> 4), pad 1, on the GN+SiLU'd bf16 NHWC operand -> NCHW fp32 velocity (unet.py:591-595).
+// One warp per output pixel, lane = 8-channel slice; weights [4][9][C] fp32 in shared memory.
+__global__ void __launch_bounds__(256)
+conv_out_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ Wr /*[4][9][C]*/,
+                const float* __restrict__ bias, float* __restrict__ v_out, int B, int H, int W, int C) {
+    extern __shared__ float s_w[];
+    for (int i = threadIdx.x; i < 36 * C; i += blockDim.x) s_w[i] = Wr[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = B * H * W;
+    for (int pix = blockIdx.x * 8 + warp; pix < total; pix += gridDim.x * 8) {
+        const int b = pix / (H * W), h = (pix / W) % H, w = pix % W;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int tap = 0; tap < 9; ++tap) {
+            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;  // warp-uniform
+            const __nv_bfloat16* ap = a + (static_cast<size_t>(b) * H * W + static_cast<size_t>(hh) * W + ww) * C;
+            for (int c0 = lane * 8; c0 < C; c0 += 256) {
+                const uint4 u = *reinterpret_cast<const uint4*>(ap + c0);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+                float f[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 t = __bfloat1622float2(h2[k]);
+                    f[2 * k] = t.x, f[2 * k + 1] = t.y;
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const float* wp = s_w + (o * 9 + tap) * C + c0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[o] = fmaf(f[k], wp[k], acc[o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
+        if (lane < 4) {
+            const float r = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+            v_out[((static_cast<size_t>(b) * 4 + lane) * H + h) * W + w] = r + bias[lane];
+        }
+    }
+}
+
+// Upsample: nearest x2 of the fp32 stream -> bf16 operand of the following conv3x3 (unet.py:92-99).
+__global__ void upsample2x_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C) {
+    const size_t n4 = static_cast<size_t>(B) * 2 * H * 2 * W * (C / 4);
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int c4 = static_cast<int>(i % (C / 4));
+    size_t r = i / (C / 4);
+    const int w2 = static_cast<int>(r % (2 * W));
+    r /= (2 * W);
+    const int h2 = static_cast<int>(r % (2 * H));
+    const int b = static_cast<int>(r / (2 * H));
+    const float4 v = *reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * H + h2 / 2) * W + w2 / 2) * C + c4 * 4);
+    *reinterpret_cast<uint2*>(y + i * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+// ------------------------------------------------------------------------------------------------
+// AttentionBlock core (QKVAttentionLegacy, unet.py:319-334) for the short token grids of the UNet (T <= 256).
+// qkv: bf16 [B*T, 3C] with channel = head*3ch + {q,k,v}*ch + c ; out: bf16 [B*T, C] with channel = head*ch + c.
+// One warp per query; lanes split the keys for the scores and the channels for the output.  fp32 softmax.
+__global__ void __launch_bounds__(256)
+attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int C, int heads) {
+    __shared__ float s_q[8][256];
+    __shared__ float s_p[8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / heads, head = blockIdx.x % heads;
+    const int ch = C / heads;
+    const int t = blockIdx.y * 8 + warp;
+    if (t >= T) return;
+    const size_t ld = static_cast<size_t>(3) * C;
+    const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * T * ld + static_cast<size_t>(head) * 3 * ch;
+    const float scale2 = rsqrtf(static_cast<float>(ch));  // (ch^-1/4)^2
+    for (int c = lane; c < ch; c += 32) s_q[warp][c] = __bfloat162float(base[static_cast<size_t>(t) * ld + c]);
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int s = lane; s < T; s += 32) {
+        const __nv_bfloat16* kp = base + static_cast<size_t>(s) * ld + ch;
+        float acc = 0.f;
+        for (int c = 0; c < ch; c += 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(kp + c);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(h2[k]);
+                acc = fmaf(s_q[warp][c + 2 * k], f.x, acc);
+                acc = fmaf(s_q[warp][c + 2 * k + 1], f.y, acc);
+            }
+        }
+        acc *= scale2;
+        s_p[warp][s] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < T; s += 32) {
+        const float p = __expf(s_p[warp][s] - mx);
+        s_p[warp][s] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    // output channels: lane handles c = 2*lane + 64*m
+    for (int c0 = 2 * lane; c0 < ch; c0 += 64) {
+        float a0 = 0.f, a1 = 0.f;
+        const __nv_bfloat16* vp = base + 2 * ch + c0;
+        for (int s = 0; s < T; ++s) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vp + static_cast<size_t>(s) * ld));
+            const float p = s_p[warp][s];
+            a0 = fmaf(p, f.x, a0);
+            a1 = fmaf(p, f.y, a1);
+        }
+        *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * T + t) * C + head * ch + c0) = pack_bf16x2(a0 * inv, a1 * inv);
+    }
+}
+
+// conv weight repack: [Cout, Cin, 3, 3] fp32 -> [Cout, 3, 3, Cin] bf16 (K index = (r*3+s)*Cin + c, K-major rows)
+__global__ void conv_weight_repack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps) {
+    const size_t n = static_cast<size_t>(Cout) * Cin * taps;
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = static_cast<int>(i % Cin);
+    const int tap = static_cast<int>((i / Cin) % taps);
+    const int o = static_cast<int>(i / (static_cast<size_t>(Cin) * taps));
+    out[i] = __float2bfloat16(w[(static_cast<size_t>(o) * Cin + c) * taps + tap]);
+}
+// out.2 weight repack: [4, C, 3, 3] fp32 -> [4][9][C] fp32
+__global__ void conv_out_weight_repack_kernel(const float* __restrict__ w, float* __restrict__ out, int C) {
+    const int n = 4 * 9 * C;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = i % C, tap = (i / C) % 9, o = i / (9 * C);
+    out[i] = w[(static_cast<size_t>(o) * C + c) * 9 + tap];
+}
+
+// sinusoidal timestep features of arbitrary even width (nn.py:103-121; cos first, raw t)
+__global__ void timestep_features_dim_kernel(const float* __restrict__ t, int t_numel, float* __restrict__ tf, int B, int dim) {
+    const int b = blockIdx.x;
+    const int half = dim / 2;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        const float tv = t[t_numel == 1 ? 0 : b];
+        const int k = i < half ? i : i - half;
+        const float freq = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+        const float a = tv * freq;
+        tf[static_cast<size_t>(b) * dim + i] = (i < half) ? cosf(a) : sinf(a);
+    }
+}
+
+// general skinny linear (any K % 4 == 0): out[b, j] = act(bias[j] + W[j,:] . in[b,:] (+ table[idx[b], j]))
+// mode 0: SiLU -> fp32;  mode 1: (+table) then SiLU -> bf16
+__global__ void __launch_bounds__(256)
+skinny_linear_gen_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ in, int B,
+                         int N, int K, const float* __restrict__ table, const long long* __restrict__ idx, int mode,
+                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= N) return;
+    const float4* wp = reinterpret_cast<const float4*>(W + static_cast<size_t>(j) * K);
+    const float bj = bias[j];
+    for (int b = 0; b < B; ++b) {
+        const float4* ip = reinterpret_cast<const float4*>(in + static_cast<size_t>(b) * K);
+        float acc = 0.f;
+        for (int m = lane; m < K / 4; m += 32) {
+            const float4 w4 = __ldg(wp + m), x4 = __ldg(ip + m);
+            acc = fmaf(w4.x, x4.x, acc);
+            acc = fmaf(w4.y, x4.y, acc);
+            acc = fmaf(w4.z, x4.z, acc);
+            acc = fmaf(w4.w, x4.w, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float v = acc + bj;
+            if (mode == 1 && table != nullptr && idx != nullptr) v += table[static_cast<size_t>(idx[b]) * N + j];
+            v = silu(v);
+            if (mode == 0)
+                out_f32[static_cast<size_t>(b) * N + j] = v;
+            else
+                out_bf16[static_cast<size_t>(b) * N + j] = __float2bfloat16(v);
+        }
+    }
+}
+
+}  // namespace lfm

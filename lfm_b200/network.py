@@ -38,7 +38,96 @@ class _Holder(nn.Module):
     """Parameter container: exists only so that state_dict keys match the reference's module tree."""
 
 
-class DiT(nn.Module):
+class _NativeNet(nn.Module):
+    """Shared plumbing: lazily create the native context, upload the state_dict (strict), call lfm_forward."""
+
+    max_batch_hint = None
+    table_rows = 0
+
+    def _init_native(self):
+        self._ctx = None
+        self._ctx_rows = 0
+        self._ctx_device = None
+        self._uploaded_version = None
+        self.last_stats = None
+
+    def _version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _release(self):
+        if getattr(self, "_ctx", None) is not None:
+            _lib.load().lfm_destroy(self._ctx)
+            self._ctx = None
+            self._ctx_rows = 0
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _create_ctx(self, lib, dev_index):  # -> ctypes handle
+        raise NotImplementedError
+
+    def native(self, rows: int, device: torch.device):
+        """Return the lfm_ctx handle, (re)creating it and uploading the weights when needed."""
+        lib = _lib.load()
+        if device.type != "cuda":
+            raise RuntimeError("lfm_b200 runs on a CUDA device (B200, sm_100a) only; got tensors on " + str(device))
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        ver = self._version()
+        if (self._ctx is not None and rows <= self._ctx_rows and self._ctx_device == dev_index
+                and ver == self._uploaded_version):
+            return self._ctx
+        self._release()
+        ctx = self._create_ctx(lib, dev_index)
+        try:
+            for key, p in self.state_dict().items():
+                t = p.detach().to(torch.float32).contiguous()
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                _lib.check(lib.lfm_set_param(ctx, key.encode(), C.c_void_p(t.data_ptr()), 0, shape, t.dim()), ctx)
+            max_rows = max(rows, self.max_batch_hint or 0)
+            _lib.check(lib.lfm_finalize(ctx, max_rows), ctx)
+        except Exception:
+            lib.lfm_destroy(ctx)
+            raise
+        self._ctx, self._ctx_rows, self._ctx_device, self._uploaded_version = ctx, max_rows, dev_index, ver
+        return ctx
+
+    @staticmethod
+    def _stream(device):
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+    def _prep(self, t, x, y):
+        if not x.is_cuda:
+            raise RuntimeError("lfm_b200: x must be a CUDA tensor (no CPU path)")
+        x = x.to(torch.float32).contiguous()
+        B = x.shape[0]
+        t = torch.as_tensor(t, dtype=torch.float32, device=x.device).reshape(-1).contiguous()
+        if t.numel() not in (1, B):
+            raise ValueError(f"t has {t.numel()} elements, expected 1 or {B}")
+        if y is not None:
+            y = torch.as_tensor(y, device=x.device).to(torch.int64).contiguous()
+            if y.numel() != B:
+                raise ValueError(f"y has {y.numel()} labels, expected {B}")
+            # same failure the reference's nn.Embedding would raise on an out-of-range label
+            if int(y.min()) < 0 or int(y.max()) >= self.table_rows:
+                raise IndexError("label out of range for the embedding table")
+        return t, x, y, B
+
+    def _forward_native(self, t, x, y, cfg_scale=1.0):
+        B = x.shape[0]
+        ctx = self.native(B, x.device)
+        v = torch.empty_like(x)
+        _lib.check(_lib.load().lfm_forward(ctx, t.data_ptr(), t.numel(), x.data_ptr(), y.data_ptr() if y is not None else None,
+                                           B, float(cfg_scale), v.data_ptr(), self._stream(x.device)), ctx)
+        return v
+
+    def launch_count(self) -> int:
+        return int(_lib.load().lfm_launch_count(self._ctx)) if self._ctx is not None else 0
+
+
+class DiT(_NativeNet):
     """B200-native DiT velocity network with the reference's constructor (models/DiT.py:157-169)."""
 
     def __init__(self, img_resolution=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28, num_heads=16,
@@ -79,11 +168,7 @@ class DiT(nn.Module):
         self.final_layer.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(D, 2 * D))
         self.initialize_weights()
         self.requires_grad_(False)
-        self._ctx = None
-        self._ctx_rows = 0
-        self._ctx_device = None
-        self._uploaded_version = None
-        self.last_stats = None
+        self._init_native()
 
     # -- reference models/DiT.py:193-228 (same distributions; adaLN and output layers start at zero) ----------
     def initialize_weights(self):
@@ -106,79 +191,17 @@ class DiT(nn.Module):
         nn.init.zeros_(self.final_layer.linear.weight)
         nn.init.zeros_(self.final_layer.linear.bias)
 
-    # -- native context management --------------------------------------------------------------------------
-    def _version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
-
-    def _release(self):
-        if self._ctx is not None:
-            _lib.load().lfm_destroy(self._ctx)
-            self._ctx = None
-            self._ctx_rows = 0
-
-    def __del__(self):
-        try:
-            self._release()
-        except Exception:
-            pass
-
-    def native(self, rows: int, device: torch.device):
-        """Return the lfm_ctx handle, (re)creating it and uploading the weights when needed."""
-        lib = _lib.load()
-        if device.type != "cuda":
-            raise RuntimeError("lfm_b200 runs on a CUDA device (B200, sm_100a) only; got tensors on " + str(device))
-        dev_index = device.index if device.index is not None else torch.cuda.current_device()
-        ver = self._version()
-        if (self._ctx is not None and rows <= self._ctx_rows and self._ctx_device == dev_index
-                and ver == self._uploaded_version):
-            return self._ctx
-        self._release()
+    def _create_ctx(self, lib, dev_index):
         desc = _lib.ModelDesc(0, self.img_resolution, self.patch_size, self.in_channels, self.hidden_size, self.depth,
                               self.num_heads, self.mlp_hidden, self.table_rows)
         ctx = C.c_void_p()
         _lib.check(lib.lfm_create(C.byref(desc), dev_index, C.byref(ctx)))
-        try:
-            for key, p in self.state_dict().items():
-                t = p.detach().to(torch.float32).contiguous()
-                shape = (C.c_int64 * t.dim())(*t.shape)
-                _lib.check(lib.lfm_set_param(ctx, key.encode(), C.c_void_p(t.data_ptr()), 0, shape, t.dim()), ctx)
-            max_rows = max(rows, self.max_batch_hint or 0)
-            _lib.check(lib.lfm_finalize(ctx, max_rows), ctx)
-        except Exception:
-            lib.lfm_destroy(ctx)
-            raise
-        self._ctx, self._ctx_rows, self._ctx_device, self._uploaded_version = ctx, max_rows, dev_index, ver
         return ctx
-
-    @staticmethod
-    def _stream(device):
-        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-
-    def _prep(self, t, x, y):
-        if not x.is_cuda:
-            raise RuntimeError("lfm_b200.DiT: x must be a CUDA tensor (no CPU path)")
-        x = x.to(torch.float32).contiguous()
-        B = x.shape[0]
-        t = torch.as_tensor(t, dtype=torch.float32, device=x.device).reshape(-1).contiguous()
-        if t.numel() not in (1, B):
-            raise ValueError(f"t has {t.numel()} elements, expected 1 or {B}")
-        if y is not None:
-            y = torch.as_tensor(y, device=x.device).to(torch.int64).contiguous()
-            if y.numel() != B:
-                raise ValueError(f"y has {y.numel()} labels, expected {B}")
-            # same failure the reference's nn.Embedding would raise on an out-of-range label
-            if int(y.min()) < 0 or int(y.max()) >= self.table_rows:
-                raise IndexError("label out of range for the embedding table")
-        return t, x, y, B
 
     # -- model(t, x, y)  (reference models/DiT.py:252-272) -----------------------------------------------------
     def forward(self, t, x, y=None, **kwargs):
         t, x, y, B = self._prep(t, x, y)
-        ctx = self.native(B, x.device)
-        v = torch.empty_like(x)
-        _lib.check(_lib.load().lfm_forward(ctx, t.data_ptr(), t.numel(), x.data_ptr(), y.data_ptr() if y is not None else None,
-                                           B, 1.0, v.data_ptr(), self._stream(x.device)), ctx)
-        return v
+        return self._forward_native(t, x, y)
 
     # -- model.forward_with_cfg(t, x, y, cfg_scale)  (reference models/DiT.py:274-290) ------------------------
     def forward_with_cfg(self, t, x, y=None, cfg_scale=1.0, **kwargs):
@@ -187,22 +210,14 @@ class DiT(nn.Module):
             raise ValueError("forward_with_cfg expects the doubled batch [x, x]")
         if y is None:
             y = torch.full((B,), self.table_rows - 1, dtype=torch.int64, device=x.device)
-        ctx = self.native(B, x.device)
-        v = torch.empty_like(x)
         if cfg_scale > 1.0:
-            _lib.check(_lib.load().lfm_forward(ctx, t.data_ptr(), t.numel(), x.data_ptr(), y.data_ptr(), B, float(cfg_scale),
-                                               v.data_ptr(), self._stream(x.device)), ctx)
-            return v
+            return self._forward_native(t, x, y, cfg_scale)
         # cfg_scale <= 1: g = u + s (c - u) still holds; evaluate the plain doubled batch and combine here
         half = x[: B // 2]
         out = self.forward(t, torch.cat([half, half], 0), y)
         c, u = out[: B // 2], out[B // 2:]
         g = u + cfg_scale * (c - u)
         return torch.cat([g, g], 0)
-
-    def launch_count(self) -> int:
-        return int(_lib.load().lfm_launch_count(self._ctx)) if self._ctx is not None else 0
-
 
 def _dit(depth, hidden_size, patch_size, num_heads):
     def make(**kwargs):
@@ -234,6 +249,28 @@ def create_network(config):
 
 
 def get_flow_model(config):
-    """reference models/__init__.py:20-70 (ADM UNetModel).  Not implemented in this round - fails loudly."""
-    raise NotImplementedError("the ADM UNetModel path (models/guided_diffusion/unet.py) is not built yet; "
-                              "see DESIGN.md 'scope'")
+    """reference models/__init__.py:20-70: the OpenAI-ADM UNetModel selected by --use_origin_adm."""
+    from .unet import UNetModel
+    if getattr(config, "layout", False):
+        raise NotImplementedError("UNetModelAttn (--layout, cross-attention conditioning) is outside the hot path")
+    return UNetModel(
+        image_size=config.image_size // 8,
+        in_channels=config.num_in_channels,
+        model_channels=config.nf,
+        out_channels=config.num_out_channels,
+        num_res_blocks=config.num_res_blocks,
+        attention_resolutions=config.attn_resolutions,
+        dropout=config.dropout,
+        channel_mult=config.ch_mult,
+        conv_resample=config.resamp_with_conv,
+        dims=2,
+        num_classes=config.num_classes,
+        use_checkpoint=False,
+        use_fp16=False,
+        num_heads=config.num_heads,
+        num_head_channels=config.num_head_channels,
+        num_heads_upsample=config.num_head_upsample,
+        use_scale_shift_norm=config.use_scale_shift_norm,
+        resblock_updown=config.resblock_updown,
+        use_new_attention_order=config.use_new_attention_order,
+    )

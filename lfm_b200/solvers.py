@@ -19,7 +19,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .network import DiT
+from .network import _NativeNet
 
 ADAPTIVE_SOLVER = ["dopri5", "dopri8", "adaptive_heun", "bosh3"]   # test_flow_latent.py:27
 FIXER_SOLVER = ["euler", "rk4", "midpoint", "stochastic"]         # test_flow_latent.py:28
@@ -32,9 +32,9 @@ HEUN_REFERENCE_CORRECTOR_LIMIT = 39
 def _unwrap(model):
     """Accept the NFECount-style wrappers of the reference CLI (attribute .model)."""
     inner = model
-    while not isinstance(inner, DiT) and hasattr(inner, "model"):
+    while not isinstance(inner, _NativeNet) and hasattr(inner, "model"):
         inner = inner.model
-    if not isinstance(inner, DiT):
+    if not isinstance(inner, _NativeNet):
         raise TypeError("lfm_b200 solvers need an lfm_b200 network (got %r)" % type(model).__name__)
     return inner
 
@@ -71,7 +71,7 @@ def _run_fixed(model, x, y, cfg_scale, t_nodes, method, t_as_vector, corrector_l
     _lib.check(_lib.load().lfm_sample_fixed(
         ctx, {"euler": 0, "heun": 1}[method], x.data_ptr(), grid.data_ptr(), grid.numel(), int(t_as_vector),
         int(corrector_limit), y.data_ptr() if y is not None else None, n_img, float(cfg_scale), C.byref(stats),
-        DiT._stream(x.device)), ctx)
+        _NativeNet._stream(x.device)), ctx)
     net.last_stats = dict(nfe=int(stats.nfe), accepted=int(stats.accepted), rejected=int(stats.rejected))
     return x, net.last_stats
 
@@ -115,7 +115,7 @@ def sample_from_model(model, x_0, model_kwargs, args):
         st = _lib.OdeStats()
         _lib.check(_lib.load().lfm_sample_dopri5(ctx, xf.data_ptr(), 1.0, 0.0, float(args.rtol), float(args.atol),
                                                  y.data_ptr() if y is not None else None, n_img, float(cfg_scale),
-                                                 C.byref(st), DiT._stream(xf.device)), ctx)
+                                                 C.byref(st), _NativeNet._stream(xf.device)), ctx)
         stats = dict(nfe=int(st.nfe), accepted=int(st.accepted), rejected=int(st.rejected))
         net.last_stats = stats
     else:

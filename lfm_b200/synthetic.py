@@ -31,3 +31,26 @@ def synthetic_state_dict(net, seed: int = 1) -> "dict[str, torch.Tensor]":
             a = math.sqrt(6.0 / (fan_in + fan_out))
             sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * a
     return sd
+
+
+def synthetic_unet_state_dict(net, seed: int = 1) -> "dict[str, torch.Tensor]":
+    """Same idea for the ADM UNetModel (its zero_module convs make a fresh model return 0, unet.py:198,276,594):
+    conv / linear U(-a, a) with a = 1/sqrt(fan_in); GroupNorm weight 1 + 0.1 N, bias 0.1 N; biases 0.02 N."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, p in net.state_dict().items():
+        shp = tuple(p.shape)
+        is_gn = (k.endswith("in_layers.0.weight") or k.endswith("out_layers.0.weight") or k.endswith("norm.weight")
+                 or k == "out.0.weight")
+        is_gn_b = (k.endswith("in_layers.0.bias") or k.endswith("out_layers.0.bias") or k.endswith("norm.bias")
+                   or k == "out.0.bias")
+        if is_gn:
+            sd[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif is_gn_b:
+            sd[k] = 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith(".bias") or k == "label_emb.weight":
+            sd[k] = 0.02 * torch.randn(shp, generator=g)
+        else:
+            fan_in = int(math.prod(shp[1:]))
+            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
+    return sd

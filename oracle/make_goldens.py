@@ -71,12 +71,13 @@ def build(models, kwargs, seed, factory=None):
 
 UNET_CASES = {
     # small ADM nets with the celeb512 topology rules (attention at ds 2 and 4 => 16x16 / 8x8 tokens here)
-    "unet_mini": (dict(image_size=32, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+    # (channel counts are multiples of 128, the native path's GroupNorm vector width)
+    "unet_mini": (dict(image_size=32, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=1,
                        attention_resolutions=(2, 4), channel_mult=(1, 2, 2), num_heads=2, num_head_channels=-1,
                        num_classes=None), 21, 2),
-    "unet_mini_cond": (dict(image_size=32, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=2,
-                            attention_resolutions=(4,), channel_mult=(1, 1, 2), num_heads=4, num_head_channels=-1,
-                            num_classes=7), 22, 2),
+    "unet_mini_cond": (dict(image_size=32, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=2,
+                            attention_resolutions=(4, 8), channel_mult=(1, 1, 2, 3), num_heads=4, num_head_channels=-1,
+                            num_classes=7), 22, 3),
 }
 
 
@@ -97,7 +98,7 @@ def make_unet_goldens(g):
         net.load_state_dict(sd, strict=True)   # pins the key set / shapes of oracle.unet.param_shapes
         net.eval()
         x = torch.randn(B, 4, kw["image_size"], kw["image_size"], generator=g)
-        tv = torch.tensor([0.85, 0.3][:B])
+        tv = torch.tensor([0.85, 0.3, 0.55][:B])
         out = {"x": x, "t_vec": tv, "weight_seed": np.int64(seed)}
         for k, v in kw.items():
             if v is not None and not isinstance(v, tuple):

@@ -182,6 +182,65 @@ def group_sampler():
             stats(f"tdq euler h=0.1 nfe={net.last_stats}", traj[-1].cpu(), ref)
 
 
+def group_unet():
+    import types
+    import lfm_b200
+    from oracle import unet as ounet
+    from oracle import solvers as osol
+    from tests._util import T, load_golden
+    from tests.test_oracle_unet import unet_cfg_from_golden
+    for name in ("unet_mini", "unet_mini_cond", "unet_celeb256"):
+        g = load_golden(name)
+        cfg = unet_cfg_from_golden(g) if name != "unet_celeb256" else ounet.UNetConfig(image_size=32, channel_mult=(1, 2, 2, 2))
+        sd = ounet.synthetic_state_dict(cfg, int(g["weight_seed"]))
+        net = lfm_b200.UNetModel(image_size=cfg.image_size, in_channels=4, model_channels=cfg.model_channels, out_channels=4,
+                                 num_res_blocks=cfg.num_res_blocks, attention_resolutions=cfg.attention_resolutions,
+                                 channel_mult=cfg.channel_mult, num_classes=cfg.num_classes, num_heads=cfg.num_heads,
+                                 num_head_channels=cfg.num_head_channels, use_scale_shift_norm=True)
+        net.load_state_dict(sd, strict=True)
+        net = net.to(dev)
+        x = T(g["x"]).to(dev)
+        y = T(g["y"]).to(dev) if "y" in g else None
+        v = net(T(g["t_vec"]).to(dev), x, y)
+        torch.cuda.synchronize()
+        stats(f"{name} forward", v.cpu(), T(g["v"]))
+        e = (v.cpu() - T(g["v"])).abs()
+        print("   err by sample:", e.amax(dim=(1, 2, 3)).tolist(), " by channel:", e.amax(dim=(0, 2, 3)).tolist())
+        if name == "unet_mini":
+            args = types.SimpleNamespace(method="dopri5", atol=1e-3, rtol=1e-3, cfg_scale=1.0, compute_nfe=True)
+            traj, nfe = lfm_b200.sample_from_model(net, x, {}, args)
+            ref, st = osol.tdq_dopri5(lambda tt, xx: ounet.unet_forward(sd, cfg, tt, xx), T(g["x"]), rtol=1e-3, atol=1e-3)
+            stats(f"unet dopri5 nfe={net.last_stats} oracle={st.nfe}/{st.accepted}/{st.rejected}", traj[-1].cpu(), ref)
+            out = lfm_b200.karras_sample(net, x, 4, clip_denoised=False, model_kwargs={}, sigma_min=1e-5, sigma_max=1.0, sampler="heun")
+            ref = osol.karras_sample(lambda tt, xx: ounet.unet_forward(sd, cfg, tt, xx), T(g["x"]), 4, "heun")
+            stats(f"unet heun4 nfe={net.last_stats}", out.cpu(), ref)
+    # celeb512 preset timing, B=8
+    cfg = ounet.UNetConfig()
+    with torch.device("meta"):
+        net = lfm_b200.UNetModel(image_size=64, in_channels=4, model_channels=256, out_channels=4, num_res_blocks=2,
+                                 attention_resolutions=(16, 8), channel_mult=(1, 2, 2, 2, 4), num_heads=4, use_scale_shift_norm=True)
+    from lfm_b200.synthetic import synthetic_unet_state_dict
+    sd = synthetic_unet_state_dict(net, 1)
+    net = net.to_empty(device="cpu"); net.load_state_dict(sd, strict=True); net = net.to(dev)
+    for B in (8, 32):
+        x = torch.randn(B, 4, 64, 64, device=dev)
+        t = torch.tensor(0.5, device=dev)
+        for _ in range(2):
+            v = net(t, x)
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(5):
+            v = net(t, x)
+        t1.record(); torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / 5
+        fl = ounet.unet_flops_per_sample(cfg) * B
+        print(f"  celeb512 UNet forward B={B}: {ms:.2f} ms  {fl/ms/1e9:.1f} TFLOP/s  finite={bool(torch.isfinite(v).all())} absmean={float(v.abs().mean()):.4f}")
+        if B == 8:
+            ref = ounet.unet_forward(sd, cfg, torch.tensor(0.5), x[:1].cpu())
+            stats("celeb512 B=8 sample 0 vs oracle", v[:1].cpu(), ref)
+
+
 def time_gemm(M, N, K, epi, bn, iters=20):
     a = torch.randn(M, K, device=dev).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
@@ -222,5 +281,5 @@ if __name__ == "__main__":
     grp = sys.argv[1]
     print(f"=== {grp} ===", flush=True)
     t = time.time()
-    {"gemm": group_gemm, "attn": group_attn, "forward": group_forward, "sampler": group_sampler, "perf": group_perf}[grp]()
+    {"gemm": group_gemm, "attn": group_attn, "forward": group_forward, "sampler": group_sampler, "perf": group_perf, "unet": group_unet}[grp]()
     print(f"=== {grp} done in {time.time()-t:.1f}s ===", flush=True)
