@@ -301,3 +301,93 @@ def test_cfg_identity_dit_b2_full(dev):
                                  model_kwargs=dict(y=torch.cat([y, ynull]), cfg_scale=1.5), sigma_min=1e-5, sigma_max=1.0,
                                  sampler="heun")
     assert net.last_stats["nfe"] == 48 and torch.isfinite(out).all() and torch.equal(out[:32], out[32:])
+
+
+# ------------------------------------------------------------------------------------------------ ADM UNetModel
+
+TOL_UNET_NFE = 1e-2   # ~60 bf16-operand convolutions per evaluation (measured 5.5e-3); SURVEY.md 8(d)
+
+
+def make_unet(cfg, sd, dev, max_batch=None):
+    net = lfm_b200.UNetModel(image_size=cfg.image_size, in_channels=4, model_channels=cfg.model_channels, out_channels=4,
+                             num_res_blocks=cfg.num_res_blocks, attention_resolutions=cfg.attention_resolutions,
+                             channel_mult=cfg.channel_mult, num_classes=cfg.num_classes, num_heads=cfg.num_heads,
+                             num_head_channels=cfg.num_head_channels, use_scale_shift_norm=True, max_batch=max_batch)
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev).eval()
+
+
+@pytest.mark.parametrize("name", ["unet_mini", "unet_mini_cond", "unet_celeb256"])
+def test_unet_forward_vs_reference_fixture(dev, name):
+    from oracle import unet as ounet
+    from tests.test_oracle_unet import unet_cfg_from_golden
+    g = load_golden(name)
+    cfg = unet_cfg_from_golden(g) if name != "unet_celeb256" else ounet.UNetConfig(image_size=32, channel_mult=(1, 2, 2, 2))
+    net = make_unet(cfg, ounet.synthetic_state_dict(cfg, int(g["weight_seed"])), dev)
+    x = T(g["x"]).to(dev)
+    y = T(g["y"]).to(dev) if "y" in g else None
+    v = net(T(g["t_vec"]).to(dev), x, y)
+    assert rel_l2(v.cpu(), g["v"]) < TOL_UNET_NFE
+    assert torch.equal(v, net(T(g["t_vec"]).to(dev), x, y))            # deterministic
+    if y is None:
+        with pytest.raises(AssertionError):
+            net(0.5, x, torch.zeros(x.shape[0], dtype=torch.long, device=dev))   # unet.py:622-624
+        # a sub-batch reproduces its rows (odd batch sizes exercise the partial 128-pixel tiles)
+        v1 = net(T(g["t_vec"])[:1].to(dev), x[:1])
+        assert rel_l2(v1.cpu(), v[:1].cpu()) < 1e-5
+    else:
+        with pytest.raises(AssertionError):
+            net(0.5, x)
+        with pytest.raises(RuntimeError):
+            net.native(x.shape[0], x.device)
+            lfm_b200.karras_sample(net, torch.cat([x, x]), 3, clip_denoised=False, sampler="euler", sigma_min=1e-5,
+                                   sigma_max=1.0, model_kwargs=dict(y=torch.cat([y, y]), cfg_scale=1.5))
+
+
+def test_unet_solvers_vs_oracle(dev):
+    from oracle import unet as ounet
+    from tests.test_oracle_unet import unet_cfg_from_golden
+    g = load_golden("unet_mini")
+    cfg = unet_cfg_from_golden(g)
+    sd = ounet.synthetic_state_dict(cfg, int(g["weight_seed"]))
+    net = make_unet(cfg, sd, dev)
+    x = T(g["x"])
+    f = lambda tt, xx: ounet.unet_forward(sd, cfg, tt, xx)  # noqa: E731
+    out = lfm_b200.karras_sample(net, x.to(dev), 4, clip_denoised=False, model_kwargs={}, sigma_min=1e-5, sigma_max=1.0,
+                                 sampler="heun")
+    assert rel_l2(out.cpu(), osol.karras_sample(f, x, 4, "heun")) < TOL_UNET_NFE and net.last_stats["nfe"] == 6
+    args = types.SimpleNamespace(method="dopri5", atol=1e-2, rtol=1e-2, cfg_scale=1.0, compute_nfe=True)
+    traj, nfe = lfm_b200.sample_from_model(net, x.to(dev), {}, args)
+    ref, st = osol.tdq_dopri5(f, x, rtol=1e-2, atol=1e-2)
+    assert rel_l2(traj[-1].cpu(), ref) < TOL_UNET_NFE
+    assert abs(int(nfe) - st.nfe) <= 6 and int(nfe) == 2 + 6 * (net.last_stats["accepted"] + net.last_stats["rejected"])
+    args = types.SimpleNamespace(method="euler", step_size=0.25, perturb=False, cfg_scale=1.0, compute_nfe=False)
+    traj = lfm_b200.sample_from_model(net, x.to(dev), {}, args)
+    assert rel_l2(traj[-1].cpu(), osol.tdq_euler(f, x, 0.25)[0]) < TOL_UNET_NFE
+
+
+def test_unet_celeb512_full_size_properties(dev):
+    """BASELINE.json configs[3] network (celeb512 preset, 64x64x4 latents): batch-independence, finiteness, one
+    oracle spot check, and a dopri5 run with a loose tolerance (NFE accounting)."""
+    from lfm_b200.synthetic import synthetic_unet_state_dict
+    from oracle import unet as ounet
+    with torch.device("meta"):
+        net = lfm_b200.UNetModel(image_size=64, in_channels=4, model_channels=256, out_channels=4, num_res_blocks=2,
+                                 attention_resolutions=(16, 8), channel_mult=(1, 2, 2, 2, 4), num_heads=4,
+                                 use_scale_shift_norm=True, max_batch=8)
+    sd = synthetic_unet_state_dict(net, 1)
+    assert len(sd) == 396
+    net = net.to_empty(device="cpu")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(8, 4, 64, 64, generator=g).to(dev)
+    v = net(torch.tensor(0.5, device=dev), x)
+    assert torch.isfinite(v).all() and float(v.abs().mean()) > 1e-2
+    assert rel_l2(net(0.5, x[2:5]).cpu(), v[2:5].cpu()) < 1e-5
+    ref = ounet.unet_forward(sd, ounet.UNetConfig(), torch.tensor(0.5), x[:1].cpu())
+    assert rel_l2(v[:1].cpu(), ref) < TOL_UNET_NFE
+    args = types.SimpleNamespace(method="dopri5", atol=5e-2, rtol=5e-2, cfg_scale=1.0, compute_nfe=True)
+    traj, nfe = lfm_b200.sample_from_model(net, x, {}, args)
+    s = net.last_stats
+    assert int(nfe) == 2 + 6 * (s["accepted"] + s["rejected"]) and torch.isfinite(traj[-1]).all()

@@ -76,7 +76,7 @@ def test_no_cpu_path():
     with pytest.raises(NotImplementedError):
         lfm_b200.karras_sample(net, x, 4, clip_denoised=True, sampler="euler")
     with pytest.raises(NotImplementedError):
-        lfm_b200.create_network(types.SimpleNamespace(use_origin_adm=True))
+        lfm_b200.create_network(types.SimpleNamespace(use_origin_adm=False, model_type="adm"))   # EDM nets
 
 
 def test_create_network_factory():
@@ -119,3 +119,32 @@ def test_all_gather_layout_world2_gloo():
     # image j of rank r lands at j * world + r (the reference's file index, test_flow_latent_ddp.py:138)
     want = [[0, 1], [100, 101], [2, 3], [102, 103], [4, 5], [104, 105]]
     assert res[0] == want and res[1] == want
+
+
+def test_unet_state_dict_surface_and_factory():
+    from oracle import unet as ounet
+    cfg = types.SimpleNamespace(use_origin_adm=True, layout=False, image_size=512, num_in_channels=4, nf=256, num_out_channels=4,
+                                num_res_blocks=2, attn_resolutions=(16, 8), dropout=0.0, ch_mult=(1, 2, 2, 2, 4),
+                                resamp_with_conv=True, num_classes=None, num_heads=4, num_head_channels=-1,
+                                num_head_upsample=-1, use_scale_shift_norm=True, resblock_updown=False,
+                                use_new_attention_order=False)
+    with torch.device("meta"):
+        net = lfm_b200.create_network(cfg)            # models/__init__.py:7-8 -> get_flow_model
+    want = ounet.param_shapes(ounet.UNetConfig())     # pinned to the reference by oracle/make_goldens.py
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert got == want and list(got) == list(want) and len(got) == 396
+    cfg.resblock_updown = True
+    with pytest.raises(NotImplementedError):
+        lfm_b200.create_network(cfg)
+    cfg.resblock_updown, cfg.layout = False, True
+    with pytest.raises(NotImplementedError):
+        lfm_b200.create_network(cfg)
+    # zero_module layers start at zero as in the reference (unet.py:198,276,594)
+    small = lfm_b200.UNetModel(image_size=32, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=1,
+                               attention_resolutions=(2,), channel_mult=(1, 2), num_heads=2, use_scale_shift_norm=True)
+    assert float(small.out[2].weight.abs().max()) == 0.0
+    from lfm_b200.synthetic import synthetic_unet_state_dict
+    sd = synthetic_unet_state_dict(small, 21)
+    ref = ounet.synthetic_state_dict(ounet.UNetConfig(image_size=32, model_channels=128, num_res_blocks=1,
+                                                      attention_resolutions=(2,), channel_mult=(1, 2), num_heads=2), 21)
+    assert all(torch.equal(sd[k], ref[k]) for k in ref)
