@@ -24,15 +24,13 @@ LFM_DEVICE float4 src2_load(const Src2& s, size_t pix, int ch) {
 // grid (nchunk, B): each block reduces a pixel range of one sample into 32 x {sum, sumsq} (fp64 bins),
 // partial[b][chunk][32][2].  One warp per pixel; lane l owns channels 128 j + 4 l .. + 3 (C % 128 == 0, so a
 // float4 never straddles a group).
-constexpr int kGnMaxJ = 24;  // C <= 3072
+constexpr int kGnMaxJ = 16;  // C <= 2048
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(Src2 s, int HW, int C, int nchunk, double* __restrict__ partial) {
-    __shared__ double bins[32][2];
+    extern __shared__ float s_part[];  // [8 warps][J][32 lanes][2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x, b = blockIdx.y;
     const int J = C / 128, cpg = C / 32;
-    if (threadIdx.x < 64) bins[threadIdx.x >> 1][threadIdx.x & 1] = 0.0;
-    __syncthreads();
     const int p0 = static_cast<int>(static_cast<long long>(HW) * chunk / nchunk);
     const int p1 = static_cast<int>(static_cast<long long>(HW) * (chunk + 1) / nchunk);
     float sum[kGnMaxJ], sq[kGnMaxJ];
@@ -52,14 +50,26 @@ gn_stats_kernel(Src2 s, int HW, int C, int nchunk, double* __restrict__ partial)
 #pragma unroll
     for (int j = 0; j < kGnMaxJ; ++j) {
         if (j < J) {
-            const int g = (128 * j + 4 * lane) / cpg;
-            atomicAdd(&bins[g][0], static_cast<double>(sum[j]));
-            atomicAdd(&bins[g][1], static_cast<double>(sq[j]));
+            float2* dst = reinterpret_cast<float2*>(s_part) + (warp * J + j) * 32 + lane;
+            *dst = make_float2(sum[j], sq[j]);
         }
     }
     __syncthreads();
-    if (threadIdx.x < 64)
-        partial[(static_cast<size_t>(b) * nchunk + chunk) * 64 + threadIdx.x] = bins[threadIdx.x >> 1][threadIdx.x & 1];
+    // fixed-order reduction: thread g owns group g = float4 slots [g*cpg/4, (g+1)*cpg/4) of every warp
+    if (threadIdx.x < 32) {
+        const int g = threadIdx.x;
+        const int q0 = g * (cpg / 4), q1 = q0 + cpg / 4;
+        double S = 0.0, Q = 0.0;
+        for (int w = 0; w < 8; ++w)
+            for (int q = q0; q < q1; ++q) {
+                const float2 v = reinterpret_cast<const float2*>(s_part)[(w * J + (q >> 5)) * 32 + (q & 31)];
+                S += static_cast<double>(v.x);
+                Q += static_cast<double>(v.y);
+            }
+        double* dst = partial + (static_cast<size_t>(b) * nchunk + chunk) * 64 + 2 * g;
+        dst[0] = S;
+        dst[1] = Q;
+    }
 }
 
 // GroupNorm apply (+ optional FiLM h*(1+scale)+shift, unet.py:230-234; + optional SiLU) -> bf16 operand.
@@ -80,6 +90,7 @@ struct GnApplyArgs {
 };
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(GnApplyArgs a) {
+    extern __shared__ float s_coef[];  // [2][C]: y = x * A[c] + Bc[c]   (GroupNorm affine and FiLM folded per channel)
     __shared__ float s_mean[32], s_rstd[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
@@ -99,34 +110,44 @@ gn_apply_kernel(GnApplyArgs a) {
     }
     __syncthreads();
     const float* film = a.film != nullptr ? a.film + static_cast<size_t>(b) * a.film_stride : nullptr;
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        const int g = c / cpg;
+        float A = s_rstd[g] * a.gamma[c];
+        float Bc = a.beta[c] - s_mean[g] * A;
+        if (film != nullptr) {  // h * (1 + scale) + shift
+            const float sc = 1.f + film[c], sh = film[a.C + c];
+            A *= sc;
+            Bc = fmaf(Bc, sc, sh);
+        }
+        s_coef[c] = A;
+        s_coef[a.C + c] = Bc;
+    }
+    __syncthreads();
     for (int p = blockIdx.x * 8 + warp; p < a.HW; p += gridDim.x * 8) {
         const size_t pix = static_cast<size_t>(b) * a.HW + p;
-        for (int j = 0; j < J; ++j) {
-            const int ch = 128 * j + 4 * lane;
-            const float4 v = src2_load(a.src, pix, ch);
-            const int g = ch / cpg;
-            const float mean = s_mean[g], rstd = s_rstd[g];
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(a.gamma + ch));
-            const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta + ch));
-            float y0 = fmaf((v.x - mean) * rstd, ga.x, be.x);
-            float y1 = fmaf((v.y - mean) * rstd, ga.y, be.y);
-            float y2 = fmaf((v.z - mean) * rstd, ga.z, be.z);
-            float y3 = fmaf((v.w - mean) * rstd, ga.w, be.w);
-            if (film != nullptr) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(film + ch));
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(film + a.C + ch));
-                y0 = fmaf(y0, 1.f + sc.x, sh.x);
-                y1 = fmaf(y1, 1.f + sc.y, sh.y);
-                y2 = fmaf(y2, 1.f + sc.z, sh.z);
-                y3 = fmaf(y3, 1.f + sc.w, sh.w);
+        for (int j0 = 0; j0 < J; j0 += 4) {
+            float4 vv[4];  // issue up to 4 independent global loads before any store
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j0 + u < J) vv[u] = src2_load(a.src, pix, 128 * (j0 + u) + 4 * lane);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + u < J) {
+                    const int ch = 128 * (j0 + u) + 4 * lane;
+                    const float4 v = vv[u];
+                    const float4 A = *reinterpret_cast<const float4*>(s_coef + ch);
+                    const float4 Bc = *reinterpret_cast<const float4*>(s_coef + a.C + ch);
+                    float y0 = fmaf(v.x, A.x, Bc.x), y1 = fmaf(v.y, A.y, Bc.y), y2 = fmaf(v.z, A.z, Bc.z), y3 = fmaf(v.w, A.w, Bc.w);
+                    if (a.act) {
+                        y0 = silu(y0), y1 = silu(y1), y2 = silu(y2), y3 = silu(y3);
+                    }
+                    *reinterpret_cast<uint2*>(a.out + pix * a.C + ch) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                    if (a.copy_out != nullptr) *reinterpret_cast<float4*>(a.copy_out + pix * a.C + ch) = v;
+                    if (a.raw_out != nullptr)
+                        *reinterpret_cast<uint2*>(a.raw_out + pix * a.C + ch) =
+                            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                }
             }
-            if (a.act) {
-                y0 = silu(y0), y1 = silu(y1), y2 = silu(y2), y3 = silu(y3);
-            }
-            *reinterpret_cast<uint2*>(a.out + pix * a.C + ch) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-            if (a.copy_out != nullptr) *reinterpret_cast<float4*>(a.copy_out + pix * a.C + ch) = v;
-            if (a.raw_out != nullptr)
-                *reinterpret_cast<uint2*>(a.raw_out + pix * a.C + ch) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
         }
     }
 }
@@ -208,6 +229,19 @@ conv_out_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ W
             v_out[((static_cast<size_t>(b) * 4 + lane) * H + h) * W + w] = r + bias[lane];
         }
     }
+}
+
+// out.2 on the tensor cores: the pair GEMM writes [B*H*W, 4] (NHWC); this scatters it to the NCHW velocity.
+__global__ void nhwc4_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int HW) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // pixel index
+    if (i >= static_cast<size_t>(B) * HW) return;
+    const float4 v = *reinterpret_cast<const float4*>(in + i * 4);
+    const size_t b = i / HW, p = i % HW;
+    float* o = out + b * 4 * HW + p;
+    o[0] = v.x;
+    o[HW] = v.y;
+    o[2 * static_cast<size_t>(HW)] = v.z;
+    o[3 * static_cast<size_t>(HW)] = v.w;
 }
 
 // Upsample: nearest x2 of the fp32 stream -> bf16 operand of the following conv3x3 (unet.py:92-99).
