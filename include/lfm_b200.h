@@ -117,9 +117,9 @@ void lfm_destroy(lfm_ctx* ctx);
 /* Number of kernels the library has launched on this ctx since creation (bench.py's gpu_launches). */
 int64_t lfm_launch_count(const lfm_ctx* ctx);
 
-/* ---- kernel-level entry points used by the parity tests (tests/test_gpu_kernels.py) ------------------- */
+/* ---- kernel-level entry points used by the parity tests (tests/test_gpu_parity.py) ------------------- */
 /* C = A[M,K] W[N,K]^T with epilogue `epi` (0 bias->bf16, 1 bias+gelu->bf16, 2 gated residual fp32, 3 bias->fp32).
- * a, w: bf16 device pointers.  block_n: 128 or 256. */
+ * a, w: bf16 device pointers.  block_n: 128 / 256 (one CTA per tile) or 512 (CTA-pair kernel, 256 x 256 tile). */
 int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float* bias, void* out, const float* gate,
                  int gate_stride, int rows_per_sample, int M, int N, int K, int epi, int block_n, void* stream);
 /* softmax(q k^T / 8) v on a [B*256, 3*D] bf16 qkv buffer -> out [B*256, D] bf16.  variant: 2 = persistent kernel (default), 0 = P in TMEM,

@@ -173,7 +173,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], box {64, 128}
                    const __grid_constant__ CUtensorMap tmap_b,   // W [N, K], box {64, 128}
                    const __grid_constant__ CUtensorMap tmap_out, // out [M, ldo]: box {128 bytes, 32 rows}, 128B swizzle
-                   int M, int N, int K, GemmEpi ep, ConvGeom cg) {
+                   const __grid_constant__ CUtensorMap tmap_bh,  // W [N, K], box {64, 64}: half-width tail tiles
+                   int M, int N, int K, GemmEpi ep, ConvGeom cg, int allow_split) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -196,8 +197,31 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
     const int m_blocks = (M + 255) / 256;
     const int num_tiles = m_blocks * n_blocks;
     const int num_kb = K / 64;
+    // Tail splitting: the tiles of the last, partially filled wave are cut into two 256 x 128 halves when that lets
+    // them finish in half a wave (e.g. 256 tiles on 74 clusters: 3 waves + 34 tiles -> 3 waves + 68 half tiles).
+    int full_count = num_tiles, num_items = num_tiles;
+    {
+        const int rem = num_tiles % num_clusters;
+        if (allow_split && num_tiles > num_clusters && rem > 0 && 2 * rem <= num_clusters) {
+            full_count = num_tiles - rem;
+            num_items = full_count + 2 * rem;
+        }
+    }
+    auto decode = [&](int w, int& m_blk, int& n_blk, int& nh, int& width) {
+        int tile = w;
+        nh = 0;
+        width = kG2BlockN;
+        if (w >= full_count) {
+            tile = full_count + ((w - full_count) >> 1);
+            nh = (w - full_count) & 1;
+            width = kG2BlockN / 2;
+        }
+        m_blk = tile / n_blocks;
+        n_blk = tile % n_blocks;
+    };
 
     if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_bh);
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
         prefetch_tmap(&tmap_out);
@@ -225,10 +249,13 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+            for (int item = cluster_id; item < num_items; item += num_clusters) {
+                int m_blk, n_blk, nh, width;
+                decode(item, m_blk, n_blk, nh, width);
+                const bool halfw = width != kG2BlockN;
                 const int row_a = m_blk * 256 + static_cast<int>(rank) * 128;
-                const int row_b = n_blk * kG2BlockN + static_cast<int>(rank) * 128;
+                const int row_b = n_blk * kG2BlockN + nh * (kG2BlockN / 2) + static_cast<int>(rank) * (width / 2);
+                const uint32_t tx_bytes = 2 * (kG2ABytes + (halfw ? kG2BBytes / 2 : kG2BBytes));
                 int img0 = 0, h0 = 0;
                 if (cg.taps != 0) {
                     img0 = row_a / cg.HW;
@@ -237,7 +264,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 int tap = 0, cb = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kG2StageBytes);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     if (cg.taps == 0) {
                         tma_load_2d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * 64, row_a);
                     } else {
@@ -249,7 +276,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                             ++tap;
                         }
                     }
-                    tma_load_2d_2sm(smem_b + stage * kG2BBytes, &tmap_b, &full_bar[stage], kb * 64, row_b);
+                    tma_load_2d_2sm(smem_b + stage * kG2BBytes, halfw ? &tmap_bh : &tmap_b, &full_bar[stage], kb * 64, row_b);
                     if (++stage == kG2Stages) {
                         stage = 0;
                         phase ^= 1;
@@ -260,12 +287,14 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA, one thread) =====================
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(256, kG2BlockN, 0, 0);
+            constexpr uint32_t idesc_full = make_idesc_bf16(256, kG2BlockN, 0, 0);
+            constexpr uint32_t idesc_half = make_idesc_bf16(256, kG2BlockN / 2, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int item = cluster_id; item < num_items; item += num_clusters) {
+                const uint32_t idesc = item >= full_count ? idesc_half : idesc_full;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kG2BlockN;
@@ -295,30 +324,34 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
         // for the gated residual (x += g * (acc + b) is applied at L2: the SM never reads x).
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
-        uint8_t* stg = smem_stage + (warp - 4) * 4096;
+        uint8_t* stg0 = smem_stage + (warp - 4) * 4096;  // one staging tile per warp (measured: a second one at the
+        constexpr int sbuf = 0;                           // cost of a pipeline stage does not pay)
         constexpr bool kBf16Out = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+            int m_blk, n_blk, nh, width;
+            decode(item, m_blk, n_blk, nh, width);
+            const int nch = width / 64;  // 32-column chunks per warp: 4 (full tile) or 2 (half-width tail tile)
             const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;  // first row of this warp
             const int row = row0 + lane;
-            const int nbase = n_blk * kG2BlockN + half * 128;
+            const int nbase = n_blk * kG2BlockN + nh * (kG2BlockN / 2) + half * (width / 2);
             const float* gate_row = nullptr;
             if (EPI == EPI_GATE_RESID_F32 && ep.gate != nullptr)  // gate == nullptr: plain residual add (gate 1)
                 gate_row = ep.gate + static_cast<size_t>((row < M ? row : M - 1) / ep.rows_per_sample) * ep.gate_stride;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kG2BlockN + half * 128;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kG2BlockN + half * (width / 2);
             uint32_t va[32], vb[32];
             float f[32];
             tmem_ld_32x32b_x32(taddr, va);
-#pragma unroll
-            for (int c = 0; c < 4; c += 2) {
+#pragma unroll 1
+            for (int c = 0; c < nch; c += 2) {
                 tmem_ld_wait();
                 tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
                 epilogue_math<EPI>(va, f, ep, nbase + c * 32, N, gate_row);
-                // staging tile free again? (the previous TMA op of this warp has finished READING it)
+                // this staging tile is free once all but the most recent TMA op of this warp have READ their tile
+                uint8_t* stg = stg0 + sbuf * 4096;
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
                 if (kBf16Out) {
@@ -332,21 +365,20 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                             tma_reduce_add_2d(&tmap_out, stg, nbase + c * 32, row0);
                         else
                             tma_store_2d(&tmap_out, stg, nbase + c * 32, row0);
-                        tma_store_commit();
                     }
+                    if (lane == 0) tma_store_commit();
                 }
                 tmem_ld_wait();
-                if (c + 2 < 4) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
+                if (c + 2 < nch) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
                 epilogue_math<EPI>(vb, f, ep, nbase + (c + 1) * 32, N, gate_row);
                 if (kBf16Out) {
                     stage_row_bf16_half(stg, lane, f, 1);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && nbase + c * 32 < N) {
-                        tma_store_2d(&tmap_out, stg, nbase + c * 32, row0);  // 64 bf16 columns x 32 rows
-                        tma_store_commit();
-                    }
+                    if (lane == 0 && nbase + c * 32 < N) tma_store_2d(&tmap_out, stg, nbase + c * 32, row0);  // 64 bf16 cols
+                    if (lane == 0) tma_store_commit();
                 } else {
+                    stg = stg0 + sbuf * 4096;
                     if (lane == 0) tma_store_wait_read<0>();
                     __syncwarp();
                     stage_row_f32(stg, lane, f);
@@ -357,8 +389,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                             tma_reduce_add_2d(&tmap_out, stg, nbase + (c + 1) * 32, row0);
                         else
                             tma_store_2d(&tmap_out, stg, nbase + (c + 1) * 32, row0);
-                        tma_store_commit();
                     }
+                    if (lane == 0) tma_store_commit();
                 }
             }
             tc_fence_before();

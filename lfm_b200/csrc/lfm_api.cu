@@ -85,6 +85,11 @@ static bool make_tmap_out(CUtensorMap* m, const void* base, uint64_t rows, uint6
     return r == CUDA_SUCCESS;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v != nullptr && *v != 0) ? atoi(v) : dflt;
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel launch helpers
 
@@ -110,7 +115,7 @@ static cudaError_t launch_gemm_inst(cudaStream_t s, const CUtensorMap& ta, const
 template <int EPI>
 static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb,
                                      const CUtensorMap& tout, int M, int N, int K, const GemmEpi& ep,
-                                     ConvGeom cg = ConvGeom{0, 0, 0, 0, 1}) {
+                                     ConvGeom cg = ConvGeom{0, 0, 0, 0, 1}, const CUtensorMap* tbh = nullptr) {
     static bool attr_set = false;
     auto kern = gemm2_bf16_tcgen05<EPI>;
     if (!attr_set) {
@@ -121,7 +126,9 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
     const int tiles = ((M + 255) / 256) * ((N + kG2BlockN - 1) / kG2BlockN);
     int clusters = g_num_sms / 2;
     if (tiles < clusters) clusters = tiles;
-    kern<<<2 * clusters, kG2Threads, kG2SmemBytes, s>>>(ta, tb, tout, M, N, K, ep, cg);
+    static const int split_env = env_int("LFM_GEMM_SPLIT", 1);
+    kern<<<2 * clusters, kG2Threads, kG2SmemBytes, s>>>(ta, tb, tout, tbh != nullptr ? *tbh : tb, M, N, K, ep, cg,
+                                                        (tbh != nullptr && split_env) ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -130,13 +137,15 @@ constexpr int kGemmPair = 512;
 static inline uint32_t weight_box_rows(int block_n) { return block_n == kGemmPair ? 128u : static_cast<uint32_t>(block_n); }
 
 static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-                               int epi, int block_n, const GemmEpi& ep, const CUtensorMap* tout = nullptr) {
+                               int epi, int block_n, const GemmEpi& ep, const CUtensorMap* tout = nullptr,
+                               const CUtensorMap* tbh = nullptr) {
     if (block_n == kGemmPair) {
         if (tout == nullptr) return cudaErrorInvalidValue;
-        if (epi == EPI_BIAS_BF16) return launch_gemm2_inst<EPI_BIAS_BF16>(s, ta, tb, *tout, M, N, K, ep);
-        if (epi == EPI_BIAS_GELU_BF16) return launch_gemm2_inst<EPI_BIAS_GELU_BF16>(s, ta, tb, *tout, M, N, K, ep);
-        if (epi == EPI_GATE_RESID_F32) return launch_gemm2_inst<EPI_GATE_RESID_F32>(s, ta, tb, *tout, M, N, K, ep);
-        if (epi == EPI_BIAS_F32) return launch_gemm2_inst<EPI_BIAS_F32>(s, ta, tb, *tout, M, N, K, ep);
+        const ConvGeom cg{0, 0, 0, 0, 1};
+        if (epi == EPI_BIAS_BF16) return launch_gemm2_inst<EPI_BIAS_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
+        if (epi == EPI_BIAS_GELU_BF16) return launch_gemm2_inst<EPI_BIAS_GELU_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
+        if (epi == EPI_GATE_RESID_F32) return launch_gemm2_inst<EPI_GATE_RESID_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
+        if (epi == EPI_BIAS_F32) return launch_gemm2_inst<EPI_BIAS_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
         return cudaErrorInvalidValue;
     }
 #define LFM_GEMM_CASE(BN, E) \
@@ -229,6 +238,7 @@ struct BlockW {
     __nv_bfloat16 *w_qkv, *w_proj, *w_fc1, *w_fc2;
     float *b_qkv, *b_proj, *b_fc1, *b_fc2;
     CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
+    CUtensorMap tmh_qkv, tmh_proj, tmh_fc1, tmh_fc2;  // box {64, 64}: half-width tail tiles of the pair GEMM
 };
 
 struct UNetState;
@@ -315,11 +325,6 @@ static void add_param(lfm_ctx* ctx, const std::string& key, void* dst, std::vect
 static void add_param_kind(lfm_ctx* ctx, const std::string& key, void* dst, std::vector<int64_t> shape, int kind) {
     add_param(ctx, key, dst, shape, kind != 0);
     ctx->params[key].kind = kind;
-}
-
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v != nullptr && *v != 0) ? atoi(v) : dflt;
 }
 
 extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out) {
@@ -537,6 +542,10 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
         ok &= make_tmap_bf16(&b.tm_proj, b.w_proj, D, D, weight_box_rows(ctx->bn_proj));
         ok &= make_tmap_bf16(&b.tm_fc1, b.w_fc1, Hd, D, weight_box_rows(ctx->bn_fc1));
         ok &= make_tmap_bf16(&b.tm_fc2, b.w_fc2, D, Hd, weight_box_rows(ctx->bn_fc2));
+        ok &= make_tmap_bf16(&b.tmh_qkv, b.w_qkv, 3 * D, D, 64);
+        ok &= make_tmap_bf16(&b.tmh_proj, b.w_proj, D, D, 64);
+        ok &= make_tmap_bf16(&b.tmh_fc1, b.w_fc1, Hd, D, 64);
+        ok &= make_tmap_bf16(&b.tmh_fc2, b.w_fc2, D, Hd, 64);
     }
     if (!ok) return fail(ctx, "lfm_finalize: cuTensorMapEncodeTiled failed");
     ctx->max_rows = R;
@@ -588,7 +597,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         ctx->launches++;
         {
             GemmEpi ep{b.b_qkv, ctx->qkv, 3 * D, nullptr, 0, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv));
+            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv, &b.tmh_qkv));
             ctx->launches++;
         }
         if (ctx->attn_variant == 2)
@@ -600,19 +609,19 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         ctx->launches++;
         {
             GemmEpi ep{b.b_proj, ctx->x_tok, D, mb + 2 * D, Nmod, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok));
+            CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok, &b.tmh_proj));
             ctx->launches++;
         }
         CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D));
         ctx->launches++;
         {
             GemmEpi ep{b.b_fc1, ctx->hmid, Hd, nullptr, 0, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_fc1, M, Hd, D, EPI_BIAS_GELU_BF16, ctx->bn_fc1, ep, &ctx->tmo_hmid));
+            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_fc1, M, Hd, D, EPI_BIAS_GELU_BF16, ctx->bn_fc1, ep, &ctx->tmo_hmid, &b.tmh_fc1));
             ctx->launches++;
         }
         {
             GemmEpi ep{b.b_fc2, ctx->x_tok, D, mb + 5 * D, Nmod, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep, &ctx->tmo_xtok));
+            CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep, &ctx->tmo_xtok, &b.tmh_fc2));
             ctx->launches++;
         }
     }
@@ -1062,7 +1071,9 @@ extern "C" int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float*
     GemmEpi ep{bias, out, N, gate, gate_stride, rows_per_sample > 0 ? rows_per_sample : 1};
     CUtensorMap tout;
     if (!make_tmap_out(&tout, out, M, N, epi >= 2)) return fail(ctx, "lfm_dbg_gemm: output tensor map encode failed");
-    CUDA_OK(launch_gemm(static_cast<cudaStream_t>(stream), ta, tb, M, N, K, epi, block_n, ep, &tout));
+    CUtensorMap tbh;
+    if (!make_tmap_bf16(&tbh, w_bf16, N, K, 64)) return fail(ctx, "lfm_dbg_gemm: tensor map encode failed");
+    CUDA_OK(launch_gemm(static_cast<cudaStream_t>(stream), ta, tb, M, N, K, epi, block_n, ep, &tout, &tbh));
     return 0;
 }
 
