@@ -27,7 +27,7 @@ typedef struct lfm_ctx lfm_ctx;
 
 enum { LFM_ARCH_DIT = 0, LFM_ARCH_UNET = 1 };
 enum { LFM_DTYPE_F32 = 0 };
-enum { LFM_METHOD_EULER = 0, LFM_METHOD_HEUN = 1 };
+enum { LFM_METHOD_EULER = 0, LFM_METHOD_HEUN = 1, LFM_METHOD_MIDPOINT = 2, LFM_METHOD_RK4 = 3 };
 
 /* Constructor arguments of the reference network (models/DiT.py:157-169, selected by
  * models/__init__.py:12-17 create_network).  image side = grid * patch. */
@@ -98,6 +98,8 @@ int lfm_forward(lfm_ctx* ctx, const float* t, int t_numel, const float* x, const
  *                                                                   torchdiffeq fixed-grid euler (test_flow_latent.py:61-73)
  *   LFM_METHOD_HEUN   predictor + trapezoid corrector for intervals i < heun_corrector_limit, Euler beyond
  *                                                                   sampler/karras_sample.py:122-161
+ *   LFM_METHOD_MIDPOINT / LFM_METHOD_RK4   torchdiffeq's fixed-grid midpoint and rk4 (3/8 rule) step functions
+ *                                                                   (test_flow_latent.py:61-73 with --method midpoint|rk4)
  *   t_as_vector: 0 = the model sees a 0-d t (torchdiffeq), 1 = a [B] vector (Karras samplers).
  *   x_inout: [B_img, C, H, W] latents, updated in place.  y: labels, [B_img] (cfg_scale <= 1) or [2*B_img]
  *   (cfg_scale > 1: conditional labels then null labels; a 2*B_img-row network batch is evaluated per NFE).

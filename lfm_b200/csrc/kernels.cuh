@@ -432,6 +432,34 @@ __global__ void dopri_interp_kernel(const float* __restrict__ y0, const float* _
     out[i] = total;
 }
 
+// torchdiffeq fixed-grid midpoint / rk4 (3/8 rule, rk4_alt_step_func) stage arithmetic, written in the same
+// operation order as the Python expressions (real-time form: dt = t1 - t0, k = v).
+//   mode 0: out = y0 + k1 * h                        (midpoint: h = 0.5 dt)
+//   mode 1: out = y0 + dt * k2                       (midpoint result)
+//   mode 2: out = y0 + (dt * k1) * (1/3)
+//   mode 3: out = y0 + dt * (k2 - k1 * (1/3))
+//   mode 4: out = y0 + dt * ((k1 - k2) + k3)
+//   mode 5: out = y0 + ((k1 + 3 (k2 + k3)) + k4) * dt * 0.125
+__global__ void fixed_rk_stage_kernel(int mode, const float* y0 /*may alias out*/, const float* __restrict__ k1,
+                                      const float* __restrict__ k2, const float* __restrict__ k3,
+                                      const float* __restrict__ k4, float dt, float* out, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float third = static_cast<float>(1.0 / 3.0);
+    float r;
+    switch (mode) {
+        case 0: r = __fadd_rn(y0[i], __fmul_rn(k1[i], dt)); break;
+        case 1: r = __fadd_rn(y0[i], __fmul_rn(dt, k2[i])); break;
+        case 2: r = __fadd_rn(y0[i], __fmul_rn(__fmul_rn(dt, k1[i]), third)); break;
+        case 3: r = __fadd_rn(y0[i], __fmul_rn(dt, __fsub_rn(k2[i], __fmul_rn(k1[i], third)))); break;
+        case 4: r = __fadd_rn(y0[i], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[i], k2[i]), k3[i]))); break;
+        default:
+            r = __fadd_rn(y0[i], __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(k1[i], __fmul_rn(3.0f, __fadd_rn(k2[i], k3[i]))), k4[i]), dt), 0.125f));
+            break;
+    }
+    out[i] = r;
+}
+
 __global__ void axpy_kernel(const float* __restrict__ y, const float* __restrict__ f, float h, float* __restrict__ out,
                             size_t n) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;

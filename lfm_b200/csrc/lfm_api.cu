@@ -782,7 +782,7 @@ extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const 
     (void)t_as_vector;  // a [B] vector of equal times and a 0-d time give the same conditioning vector
     const int rows = cfg_scale > 1.0f ? 2 * B_img : B_img;
     if (check_ready(ctx, rows, "lfm_sample_fixed")) return 1;
-    if (method != LFM_METHOD_EULER && method != LFM_METHOD_HEUN) return fail(ctx, "lfm_sample_fixed: unknown method %d", method);
+    if (method < LFM_METHOD_EULER || method > LFM_METHOD_RK4) return fail(ctx, "lfm_sample_fixed: unknown method %d", method);
     if (n_grid < 2 || n_grid > 8192) return fail(ctx, "lfm_sample_fixed: n_grid must be in [2, 8192] (got %d)", n_grid);
     if (x_inout == nullptr || t_grid_host == nullptr) return fail(ctx, "lfm_sample_fixed: null tensor");
     if (cfg_scale > 1.0f && y == nullptr) return fail(ctx, "lfm_sample_fixed: CFG needs labels");
@@ -790,6 +790,78 @@ extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const 
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)B_img * ctx->chw;
     const bool has_y = y != nullptr;
+
+    if (method == LFM_METHOD_MIDPOINT || method == LFM_METHOD_RK4) {
+        // torchdiffeq fixed-grid midpoint / rk4: the stage times of the whole trajectory are computed here in fp32
+        // exactly as the Python expressions do (t0 + dt * (1/3) ...), uploaded once, and the stages are launched
+        // back to back - no host synchronisation inside the loop.
+        if (join_in(ctx, user)) return 1;
+        cudaStream_t s = ctx->stream;
+        const int n_int = n_grid - 1, S = method == LFM_METHOD_RK4 ? 4 : 2;
+        if (n_int * S > 8192) return fail(ctx, "lfm_sample_fixed: too many stages (%d)", n_int * S);
+        std::vector<float> tg(n_grid);
+        CUDA_OK(cudaMemcpy(tg.data(), t_grid_host, n_grid * sizeof(float), cudaMemcpyDefault));
+        std::vector<float> ts((size_t)n_int * S);
+        const float third = (float)(1.0 / 3.0), two_thirds = (float)(2.0 / 3.0);
+        for (int i = 0; i < n_int; ++i) {
+            const float t0 = tg[i], t1 = tg[i + 1], dt = t1 - t0;
+            if (S == 2) {
+                ts[2 * i] = t0;
+                ts[2 * i + 1] = t0 + 0.5f * dt;
+            } else {
+                ts[4 * i] = t0;
+                ts[4 * i + 1] = t0 + dt * third;
+                ts[4 * i + 2] = t0 + dt * two_thirds;
+                ts[4 * i + 3] = t1;
+            }
+        }
+        CUDA_OK(cudaMemcpyAsync(ctx->t_grid, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(ctx->x_state, x_inout, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        const long long* yb = nullptr;
+        if (has_y) {
+            CUDA_OK(cudaMemcpyAsync(ctx->y_buf, y, (size_t)rows * sizeof(long long), cudaMemcpyDefault, s));
+            yb = ctx->y_buf;
+        }
+        CUDA_OK(cudaStreamSynchronize(s));  // ts is host stack/heap memory
+        float* y0 = ctx->x_state;
+        float* ytmp = ctx->x_pred;
+        float** k = ctx->kbuf;
+        int64_t nfe = 0;
+        for (int i = 0; i < n_int; ++i) {
+            const float dt = tg[i + 1] - tg[i];
+            const float* tp = ctx->t_grid + (size_t)i * S;
+            if (S == 2) {
+                if (eval_velocity(ctx, s, tp, 1, y0, B_img, yb, cfg_scale, k[0])) return 1;
+                fixed_rk_stage_kernel<<<blocks_for(n), 256, 0, s>>>(0, y0, k[0], nullptr, nullptr, nullptr, 0.5f * dt, ytmp, n);
+                LAUNCH_OK();
+                if (eval_velocity(ctx, s, tp + 1, 1, ytmp, B_img, yb, cfg_scale, k[1])) return 1;
+                fixed_rk_stage_kernel<<<blocks_for(n), 256, 0, s>>>(1, y0, nullptr, k[1], nullptr, nullptr, dt, y0, n);
+                LAUNCH_OK();
+            } else {
+                if (eval_velocity(ctx, s, tp, 1, y0, B_img, yb, cfg_scale, k[0])) return 1;
+                fixed_rk_stage_kernel<<<blocks_for(n), 256, 0, s>>>(2, y0, k[0], nullptr, nullptr, nullptr, dt, ytmp, n);
+                LAUNCH_OK();
+                if (eval_velocity(ctx, s, tp + 1, 1, ytmp, B_img, yb, cfg_scale, k[1])) return 1;
+                fixed_rk_stage_kernel<<<blocks_for(n), 256, 0, s>>>(3, y0, k[0], k[1], nullptr, nullptr, dt, ytmp, n);
+                LAUNCH_OK();
+                if (eval_velocity(ctx, s, tp + 2, 1, ytmp, B_img, yb, cfg_scale, k[2])) return 1;
+                fixed_rk_stage_kernel<<<blocks_for(n), 256, 0, s>>>(4, y0, k[0], k[1], k[2], nullptr, dt, ytmp, n);
+                LAUNCH_OK();
+                if (eval_velocity(ctx, s, tp + 3, 1, ytmp, B_img, yb, cfg_scale, k[3])) return 1;
+                fixed_rk_stage_kernel<<<blocks_for(n), 256, 0, s>>>(5, y0, k[0], k[1], k[2], k[3], dt, y0, n);
+                LAUNCH_OK();
+            }
+            nfe += S;
+        }
+        CUDA_OK(cudaMemcpyAsync(x_inout, y0, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (join_out(ctx, user)) return 1;
+        if (stats != nullptr) {
+            stats->nfe = nfe;
+            stats->accepted = n_int;
+            stats->rejected = 0;
+        }
+        return 0;
+    }
 
     // build (or fetch) the step graphs first: the warm-up run clobbers the solver state
     cudaGraphExec_t g_euler = nullptr, g_heun = nullptr;

@@ -69,7 +69,7 @@ def _run_fixed(model, x, y, cfg_scale, t_nodes, method, t_as_vector, corrector_l
     grid = t_nodes.detach().to("cpu", torch.float32).contiguous()
     stats = _lib.OdeStats()
     _lib.check(_lib.load().lfm_sample_fixed(
-        ctx, {"euler": 0, "heun": 1}[method], x.data_ptr(), grid.data_ptr(), grid.numel(), int(t_as_vector),
+        ctx, {"euler": 0, "heun": 1, "midpoint": 2, "rk4": 3}[method], x.data_ptr(), grid.data_ptr(), grid.numel(), int(t_as_vector),
         int(corrector_limit), y.data_ptr() if y is not None else None, n_img, float(cfg_scale), C.byref(stats),
         _NativeNet._stream(x.device)), ctx)
     net.last_stats = dict(nfe=int(stats.nfe), accepted=int(stats.accepted), rejected=int(stats.rejected))
@@ -104,6 +104,11 @@ def sample_from_model(model, x_0, model_kwargs, args):
             raise NotImplementedError("perturb=True is not implemented natively")
         nodes = euler_time_grid(float(args.step_size))
         xf, stats = _run_fixed(model, x, y, cfg_scale, nodes, "euler", 0, 0)
+    elif method in ("midpoint", "rk4"):
+        if getattr(args, "perturb", False):
+            raise NotImplementedError("perturb=True is not implemented natively")
+        nodes = euler_time_grid(float(args.step_size))
+        xf, stats = _run_fixed(model, x, y, cfg_scale, nodes, method, 0, 0)
     elif method == "dopri5":
         net = _unwrap(model)
         xf = x.to(torch.float32).contiguous().clone()
@@ -119,7 +124,7 @@ def sample_from_model(model, x_0, model_kwargs, args):
         stats = dict(nfe=int(st.nfe), accepted=int(st.accepted), rejected=int(st.rejected))
         net.last_stats = stats
     else:
-        raise NotImplementedError(f"method '{method}' has no native implementation (euler and dopri5 do)")
+        raise NotImplementedError(f"method '{method}' has no native implementation (euler, midpoint, rk4 and dopri5 do)")
     if doubled:
         xf = torch.cat([xf, xf], 0)
     traj = torch.stack([x_0.to(xf.dtype), xf], 0)

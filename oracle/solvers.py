@@ -103,6 +103,40 @@ def tdq_euler(f, x0, step_size: float, t0: float = 1.0, t1: float = 0.0):
     return y, len(tk) - 1
 
 
+@torch.no_grad()
+def tdq_fixed_rk(f, x0, step_size: float, method: str, t0: float = 1.0, t1: float = 0.0):
+    """torchdiffeq fixed-grid ``midpoint`` / ``rk4`` (v0.2.3 fixed_grid.py; ``rk4`` is the 3/8-rule
+    ``rk4_alt_step_func``) on the same grid as :func:`tdq_euler`.  Integrates s = -t with the field -f(-s, y);
+    stage times and dt are fp32 tensors, ``_one_third`` / ``_two_thirds`` python floats.  Returns (x_final, nfe)."""
+    tk = tdq_euler_grid(step_size, t0, t1)
+    sk = -tk
+    nfe = [0]
+
+    def ft(s, y):  # wrapped field in negated time
+        nfe[0] += 1
+        return -f(-s, y)
+
+    y = x0
+    one_third, two_thirds = 1.0 / 3.0, 2.0 / 3.0
+    for k in range(len(tk) - 1):
+        s0, s1 = sk[k], sk[k + 1]
+        dt = s1 - s0
+        if method == "midpoint":
+            half_dt = 0.5 * dt
+            f0 = ft(s0, y)
+            y_mid = y + f0 * half_dt
+            y = y + dt * ft(s0 + half_dt, y_mid)
+        elif method == "rk4":
+            k1 = ft(s0, y)
+            k2 = ft(s0 + dt * one_third, y + dt * k1 * one_third)
+            k3 = ft(s0 + dt * two_thirds, y + dt * (k2 - k1 * one_third))
+            k4 = ft(s1, y + dt * (k1 - k2 + k3))
+            y = y + (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+        else:
+            raise KeyError(method)
+    return y, nfe[0]
+
+
 # ----------------------------------------------------------------------------------------------
 # torchdiffeq dopri5
 

@@ -214,8 +214,14 @@ def test_torchdiffeq_euler_and_dopri5_vs_oracle(dev):
     ref, st = osol.tdq_dopri5(f, x, rtol=1e-2, atol=1e-2)
     assert (net.last_stats["nfe"], net.last_stats["accepted"], net.last_stats["rejected"]) == (st.nfe, st.accepted, st.rejected)
     assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
+    for m, per in (("midpoint", 2), ("rk4", 4)):
+        args = types.SimpleNamespace(method=m, step_size=0.2, perturb=False, cfg_scale=1.0, compute_nfe=True)
+        traj, nfe = lfm_b200.sample_from_model(net, x.to(dev), {}, args)
+        ref, n = osol.tdq_fixed_rk(f, x, 0.2, m)
+        assert int(nfe) == n == 5 * per
+        assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
     with pytest.raises(NotImplementedError):
-        lfm_b200.sample_from_model(net, x.to(dev), {}, types.SimpleNamespace(method="rk4", step_size=0.1, cfg_scale=1.0))
+        lfm_b200.sample_from_model(net, x.to(dev), {}, types.SimpleNamespace(method="bosh3", step_size=0.1, cfg_scale=1.0))
 
 
 def test_dopri5_with_cfg_vs_oracle(dev):

@@ -103,3 +103,24 @@ def test_dopri5_vs_scipy_rk45_nonlinear():
                     method="RK45", rtol=1e-10, atol=1e-12)
     assert np.allclose(xf.reshape(-1).numpy(), sol.y[:, -1], rtol=2e-4, atol=2e-4)
     assert st.nfe == 2 + 6 * (st.accepted + st.rejected)
+
+
+def test_fixed_rk_orders_on_linear_field():
+    # dx/dt = a x from t=1 to 0: exact x0 exp(-a); midpoint is 2nd order, rk4 (3/8 rule) 4th order
+    a = 0.9
+    x0 = torch.randn(2, 4, 4, 4, generator=torch.Generator().manual_seed(3)).double().float()
+    exact = x0 * math.exp(-a)
+    errs = {}
+    for m, nfe_per in (("midpoint", 2), ("rk4", 4)):
+        e = []
+        for n in (5, 10):
+            xf, nfe = osol.tdq_fixed_rk(lambda t, x: a * x, x0, 1.0 / n, m)
+            assert nfe == nfe_per * n
+            e.append(float((xf - exact).abs().max()))
+        errs[m] = e
+    assert errs["midpoint"][0] / errs["midpoint"][1] > 3.0       # ~4x per halving
+    assert errs["rk4"][0] < 1e-4 and errs["rk4"][1] < 2e-5
+    # closed forms of one step: midpoint 1 + z + z^2/2, rk4 1 + z + z^2/2 + z^3/6 + z^4/24 with z = -a h
+    xf, _ = osol.tdq_fixed_rk(lambda t, x: a * x, x0, 1.0, "rk4")
+    z = -a
+    assert torch.allclose(xf, x0 * (1 + z + z * z / 2 + z ** 3 / 6 + z ** 4 / 24), rtol=1e-5, atol=1e-6)
