@@ -1,4 +1,4 @@
-"""GPU bring-up diagnostics (run on the B200 box):  python scripts/gpu_bringup.py <group>
+"""GPU bring-up diagnostics (run on the B200 box):  python tests/tools/gpu_bringup.py <group>
 Groups: gemm, attn, forward, sampler, perf.  Prints error statistics; used to localise kernel bugs."""
 import ctypes as C
 import os
@@ -8,7 +8,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from lfm_b200 import _lib  # noqa: E402
 

@@ -5,7 +5,7 @@ LOG=gpurun_out/bringup.log
 : > $LOG
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $LOG 2>&1
 for g in ${@:-gemm attn forward sampler perf}; do
-  timeout 300 python scripts/gpu_bringup.py $g >> $LOG 2>&1
+  timeout 300 python tests/tools/gpu_bringup.py $g >> $LOG 2>&1
   echo "[group $g exit $?]" >> $LOG
 done
 tail -n 150 $LOG
