@@ -84,30 +84,43 @@ patch_embed_kernel(const float* __restrict__ x, int x_rows, const float* __restr
     if (threadIdx.x < 128) {
         const int tk = threadIdx.x >> 4, e = threadIdx.x & 15;
         const int m = m0 + tk;
+        float v = 0.f;
         if (m < M) {
             const int b = (m / T) % x_rows, t = m % T;
             const int gh = t / G, gw = t % G;
             const int c = e >> 2, p = (e >> 1) & 1, q = e & 1;
-            patch[tk][e] = x[((static_cast<size_t>(b) * C + c) * HW + (2 * gh + p)) * HW + 2 * gw + q];
+            v = x[((static_cast<size_t>(b) * C + c) * HW + (2 * gh + p)) * HW + 2 * gw + q];
         }
+        patch[tk][e] = v;
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < D; d += 256) {
-        float w[16];
+    // thread = 4 consecutive features (float4 stores, 512 B per warp); the 4 x 16 weights stay in registers
+    for (int d4 = threadIdx.x; d4 < D / 4; d4 += 256) {
+        float w[4][16];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(d) * 16) + v);
-            w[4 * v] = w4.x, w[4 * v + 1] = w4.y, w[4 * v + 2] = w4.z, w[4 * v + 3] = w4.w;
-        }
-        const float bd = bias[d];
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(4 * d4 + f) * 16) + v);
+                w[f][4 * v] = w4.x, w[f][4 * v + 1] = w4.y, w[f][4 * v + 2] = w4.z, w[f][4 * v + 3] = w4.w;
+            }
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + d4);
 #pragma unroll
         for (int tk = 0; tk < 8; ++tk) {
             const int m = m0 + tk;
             if (m < M) {
-                float acc = bd;
+                float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) acc = fmaf(w[e], patch[tk][e], acc);
-                tok[static_cast<size_t>(m) * D + d] = acc + __ldg(pos + static_cast<size_t>(m % T) * D + d);
+                for (int e = 0; e < 16; ++e) {
+                    const float pe = patch[tk][e];
+                    a0 = fmaf(w[0][e], pe, a0);
+                    a1 = fmaf(w[1][e], pe, a1);
+                    a2 = fmaf(w[2][e], pe, a2);
+                    a3 = fmaf(w[3][e], pe, a3);
+                }
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(m % T) * D) + d4);
+                reinterpret_cast<float4*>(tok + static_cast<size_t>(m) * D)[d4] =
+                    make_float4(a0 + p4.x, a1 + p4.y, a2 + p4.z, a3 + p4.w);
             }
         }
     }
@@ -261,7 +274,11 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ shift,
                 v[m].w = fmaf((v[m].w - mean) * rstd, 1.f + sc.w, sh.w);
             }
         const int gh = t / G, gw = t % G;
-        for (int j = 0; j < P; ++j) {
+        // 16 dot products: per-lane partial sums, then a butterfly that halves the number of live values per step
+        // (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5): lane l ends up with output j = (l >> 1) & 15.
+        float part[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
             const float4* wp = reinterpret_cast<const float4*>(sW + static_cast<size_t>(j) * D);
             float acc = 0.f;
 #pragma unroll
@@ -273,11 +290,47 @@ final_layer_kernel(const float* __restrict__ x, const float* __restrict__ shift,
                     acc = fmaf(w4.z, v[m].z, acc);
                     acc = fmaf(w4.w, v[m].w, acc);
                 }
-            acc = warp_sum(acc);
-            if (lane == 0) {
-                const int p = j / (2 * C), q = (j / C) & 1, c = j % C;
-                v_net[((static_cast<size_t>(bidx) * C + c) * HW + (2 * gh + p)) * HW + 2 * gw + q] = acc + bias[j];
+            part[j] = acc;
+        }
+        {
+            const bool hi = lane & 16;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float send = hi ? part[i] : part[i + 8];
+                const float keep = hi ? part[i + 8] : part[i];
+                part[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
+        }
+        {
+            const bool hi = lane & 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float send = hi ? part[i] : part[i + 4];
+                const float keep = hi ? part[i + 4] : part[i];
+                part[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+        }
+        {
+            const bool hi = lane & 4;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float send = hi ? part[i] : part[i + 2];
+                const float keep = hi ? part[i + 2] : part[i];
+                part[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+        }
+        {
+            const bool hi = lane & 2;
+            const float send = hi ? part[0] : part[1];
+            const float keep = hi ? part[1] : part[0];
+            part[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+        if ((lane & 1) == 0) {
+            // output index owned by this lane: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1
+            const int j = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            const int p = j / (2 * C), q = (j / C) & 1, c = j % C;
+            v_net[((static_cast<size_t>(bidx) * C + c) * HW + (2 * gh + p)) * HW + 2 * gw + q] = part[0] + bias[j];
         }
     }
 }

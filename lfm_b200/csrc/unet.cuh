@@ -25,35 +25,41 @@ LFM_DEVICE float4 src2_load(const Src2& s, size_t pix, int ch) {
 // partial[b][chunk][32][2].  One warp per pixel; lane l owns channels 128 j + 4 l .. + 3 (C % 128 == 0, so a
 // float4 never straddles a group).
 constexpr int kGnMaxJ = 16;  // C <= 2048
+template <int J>  // J = C / 128 float4 slots per lane per pixel
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(Src2 s, int HW, int C, int nchunk, double* __restrict__ partial) {
+gn_stats_kernel(Src2 s, int HW, int nchunk, double* __restrict__ partial) {
     extern __shared__ float s_part[];  // [8 warps][J][32 lanes][2]
+    constexpr int C = J * 128, cpg = C / 32;
+    constexpr int U = J >= 8 ? 1 : (J >= 4 ? 2 : 4);  // pixels in flight per warp: ~8 independent 512 B requests
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x, b = blockIdx.y;
-    const int J = C / 128, cpg = C / 32;
     const int p0 = static_cast<int>(static_cast<long long>(HW) * chunk / nchunk);
     const int p1 = static_cast<int>(static_cast<long long>(HW) * (chunk + 1) / nchunk);
-    float sum[kGnMaxJ], sq[kGnMaxJ];
+    float sum[J], sq[J];
 #pragma unroll
-    for (int j = 0; j < kGnMaxJ; ++j) sum[j] = sq[j] = 0.f;
-    for (int p = p0 + warp; p < p1; p += 8) {
-        const size_t pix = static_cast<size_t>(b) * HW + p;
+    for (int j = 0; j < J; ++j) sum[j] = sq[j] = 0.f;
+    for (int p = p0 + warp; p < p1; p += 8 * U) {
+        float4 v[U][J];
 #pragma unroll
-        for (int j = 0; j < kGnMaxJ; ++j) {
-            if (j < J) {
-                const float4 v = src2_load(s, pix, 128 * j + 4 * lane);
-                sum[j] += (v.x + v.y) + (v.z + v.w);
-                sq[j] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        for (int u = 0; u < U; ++u) {
+            const int pp = p + 8 * u;
+            const size_t pix = static_cast<size_t>(b) * HW + (pp < p1 ? pp : p);
+#pragma unroll
+            for (int j = 0; j < J; ++j) v[u][j] = src2_load(s, pix, 128 * j + 4 * lane);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (p + 8 * u < p1) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    sum[j] += (v[u][j].x + v[u][j].y) + (v[u][j].z + v[u][j].w);
+                    sq[j] += (v[u][j].x * v[u][j].x + v[u][j].y * v[u][j].y) + (v[u][j].z * v[u][j].z + v[u][j].w * v[u][j].w);
+                }
             }
         }
     }
 #pragma unroll
-    for (int j = 0; j < kGnMaxJ; ++j) {
-        if (j < J) {
-            float2* dst = reinterpret_cast<float2*>(s_part) + (warp * J + j) * 32 + lane;
-            *dst = make_float2(sum[j], sq[j]);
-        }
-    }
+    for (int j = 0; j < J; ++j) reinterpret_cast<float2*>(s_part)[(warp * J + j) * 32 + lane] = make_float2(sum[j], sq[j]);
     __syncthreads();
     // fixed-order reduction: thread g owns group g = float4 slots [g*cpg/4, (g+1)*cpg/4) of every warp
     if (threadIdx.x < 32) {
@@ -62,9 +68,9 @@ gn_stats_kernel(Src2 s, int HW, int C, int nchunk, double* __restrict__ partial)
         double S = 0.0, Q = 0.0;
         for (int w = 0; w < 8; ++w)
             for (int q = q0; q < q1; ++q) {
-                const float2 v = reinterpret_cast<const float2*>(s_part)[(w * J + (q >> 5)) * 32 + (q & 31)];
-                S += static_cast<double>(v.x);
-                Q += static_cast<double>(v.y);
+                const float2 t = reinterpret_cast<const float2*>(s_part)[(w * J + (q >> 5)) * 32 + (q & 31)];
+                S += static_cast<double>(t.x);
+                Q += static_cast<double>(t.y);
             }
         double* dst = partial + (static_cast<size_t>(b) * nchunk + chunk) * 64 + 2 * g;
         dst[0] = S;
@@ -88,13 +94,15 @@ struct GnApplyArgs {
     float* copy_out;            // nullptr or fp32 [B, HW, C]
     __nv_bfloat16* raw_out;     // nullptr or bf16 [B, HW, C]
 };
+template <int J>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(GnApplyArgs a) {
     extern __shared__ float s_coef[];  // [2][C]: y = x * A[c] + Bc[c]   (GroupNorm affine and FiLM folded per channel)
     __shared__ float s_mean[32], s_rstd[32];
+    constexpr int C = J * 128, cpg = C / 32;
+    constexpr int JB = J >= 4 ? 4 : J;  // float4 loads issued before the first store
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    const int J = a.C / 128, cpg = a.C / 32;
     if (threadIdx.x < 32) {
         double S = 0.0, Q = 0.0;
         for (int c = 0; c < a.nchunk; ++c) {  // fixed order => deterministic
@@ -110,41 +118,43 @@ gn_apply_kernel(GnApplyArgs a) {
     }
     __syncthreads();
     const float* film = a.film != nullptr ? a.film + static_cast<size_t>(b) * a.film_stride : nullptr;
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
         float A = s_rstd[g] * a.gamma[c];
         float Bc = a.beta[c] - s_mean[g] * A;
         if (film != nullptr) {  // h * (1 + scale) + shift
-            const float sc = 1.f + film[c], sh = film[a.C + c];
+            const float sc = 1.f + film[c], sh = film[C + c];
             A *= sc;
             Bc = fmaf(Bc, sc, sh);
         }
         s_coef[c] = A;
-        s_coef[a.C + c] = Bc;
+        s_coef[C + c] = Bc;
     }
     __syncthreads();
+    const bool act = a.act != 0;
     for (int p = blockIdx.x * 8 + warp; p < a.HW; p += gridDim.x * 8) {
         const size_t pix = static_cast<size_t>(b) * a.HW + p;
-        for (int j0 = 0; j0 < J; j0 += 4) {
-            float4 vv[4];  // issue up to 4 independent global loads before any store
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+        for (int j0 = 0; j0 < J; j0 += JB) {
+            float4 vv[JB];
+#pragma unroll
+            for (int u = 0; u < JB; ++u)
                 if (j0 + u < J) vv[u] = src2_load(a.src, pix, 128 * (j0 + u) + 4 * lane);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < JB; ++u) {
                 if (j0 + u < J) {
                     const int ch = 128 * (j0 + u) + 4 * lane;
                     const float4 v = vv[u];
                     const float4 A = *reinterpret_cast<const float4*>(s_coef + ch);
-                    const float4 Bc = *reinterpret_cast<const float4*>(s_coef + a.C + ch);
+                    const float4 Bc = *reinterpret_cast<const float4*>(s_coef + C + ch);
                     float y0 = fmaf(v.x, A.x, Bc.x), y1 = fmaf(v.y, A.y, Bc.y), y2 = fmaf(v.z, A.z, Bc.z), y3 = fmaf(v.w, A.w, Bc.w);
-                    if (a.act) {
+                    if (act) {
                         y0 = silu(y0), y1 = silu(y1), y2 = silu(y2), y3 = silu(y3);
                     }
-                    *reinterpret_cast<uint2*>(a.out + pix * a.C + ch) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-                    if (a.copy_out != nullptr) *reinterpret_cast<float4*>(a.copy_out + pix * a.C + ch) = v;
+                    *reinterpret_cast<uint2*>(a.out + pix * C + ch) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                    if (a.copy_out != nullptr) *reinterpret_cast<float4*>(a.copy_out + pix * C + ch) = v;
                     if (a.raw_out != nullptr)
-                        *reinterpret_cast<uint2*>(a.raw_out + pix * a.C + ch) =
+                        *reinterpret_cast<uint2*>(a.raw_out + pix * C + ch) =
                             make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
                 }
             }
