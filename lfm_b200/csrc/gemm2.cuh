@@ -174,7 +174,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                    const __grid_constant__ CUtensorMap tmap_b,   // W [N, K], box {64, 128}
                    const __grid_constant__ CUtensorMap tmap_out, // out [M, ldo]: box {128 bytes, 32 rows}, 128B swizzle
                    const __grid_constant__ CUtensorMap tmap_bh,  // W [N, K], box {64, 64}: half-width tail tiles
-                   int M, int N, int K, GemmEpi ep, ConvGeom cg, int allow_split) {
+                   int M, int N, int K, GemmEpi ep, ConvGeom cg, int allow_split, int ksplit, int split_row_pitch) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -199,16 +199,22 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
     const int num_kb = K / 64;
     // Tail splitting: the tiles of the last, partially filled wave are cut into two 256 x 128 halves when that lets
     // them finish in half a wave (e.g. 256 tiles on 74 clusters: 3 waves + 34 tiles -> 3 waves + 68 half tiles).
-    int full_count = num_tiles, num_items = num_tiles;
-    {
+    // Split-K (ksplit > 1; used when a GEMM has far fewer tiles than SM pairs, e.g. the 4x4 / 8x8 UNet layers):
+    // work item = (tile, k-slice); every slice stores its fp32 partial tile into its own slab of a scratch buffer
+    // (row offset slice * split_row_pitch in tmap_out) and a separate kernel adds the slabs in a fixed order.
+    int full_count = num_tiles, num_items = num_tiles * ksplit;
+    if (ksplit == 1) {
         const int rem = num_tiles % num_clusters;
         if (allow_split && num_tiles > num_clusters && rem > 0 && 2 * rem <= num_clusters) {
             full_count = num_tiles - rem;
             num_items = full_count + 2 * rem;
         }
+    } else {
+        full_count = num_items;
     }
+    const int kb_per = (num_kb + ksplit - 1) / ksplit;
     auto decode = [&](int w, int& m_blk, int& n_blk, int& nh, int& width) {
-        int tile = w;
+        int tile = ksplit > 1 ? w / ksplit : w;
         nh = 0;
         width = kG2BlockN;
         if (w >= full_count) {
@@ -261,8 +267,14 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     img0 = row_a / cg.HW;
                     h0 = (row_a % cg.HW) / cg.W;
                 }
+                const int ks = ksplit > 1 ? item % ksplit : 0;
+                const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 int tap = 0, cb = 0;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                if (cg.taps != 0) {
+                    tap = kb0 / cg.cblocks;
+                    cb = kb0 % cg.cblocks;
+                }
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     if (cg.taps == 0) {
@@ -298,15 +310,17 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kG2BlockN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int ks = ksplit > 1 ? item % ksplit : 0;
+                const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + stage * kG2ABytes), 16, 1024);
                     const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * kG2BBytes), 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < 4; ++k) umma_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
                     umma_commit_2cta(&empty_bar[stage]);
-                    if (kb == num_kb - 1) umma_commit_2cta(&tmem_full[acc]);
+                    if (kb == kb1 - 1) umma_commit_2cta(&tmem_full[acc]);
                     if (++stage == kG2Stages) {
                         stage = 0;
                         phase ^= 1;
@@ -333,8 +347,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
             int m_blk, n_blk, nh, width;
             decode(item, m_blk, n_blk, nh, width);
             const int nch = width / 64;  // 32-column chunks per warp: 4 (full tile) or 2 (half-width tail tile)
-            const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;  // first row of this warp
-            const int row = row0 + lane;
+            const int row_l = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;  // first row of this warp
+            const int row = row_l + lane;
+            const int row0 = row_l + (ksplit > 1 ? (item % ksplit) * split_row_pitch : 0);  // TMA row (slab of this k-slice)
             const int nbase = n_blk * kG2BlockN + nh * (kG2BlockN / 2) + half * (width / 2);
             const float* gate_row = nullptr;
             if (EPI == EPI_GATE_RESID_F32 && ep.gate != nullptr)  // gate == nullptr: plain residual add (gate 1)

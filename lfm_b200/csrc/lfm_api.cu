@@ -115,7 +115,8 @@ static cudaError_t launch_gemm_inst(cudaStream_t s, const CUtensorMap& ta, const
 template <int EPI>
 static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb,
                                      const CUtensorMap& tout, int M, int N, int K, const GemmEpi& ep,
-                                     ConvGeom cg = ConvGeom{0, 0, 0, 0, 1}, const CUtensorMap* tbh = nullptr) {
+                                     ConvGeom cg = ConvGeom{0, 0, 0, 0, 1}, const CUtensorMap* tbh = nullptr, int ksplit = 1,
+                                     int split_row_pitch = 0) {
     static bool attr_set = false;
     auto kern = gemm2_bf16_tcgen05<EPI>;
     if (!attr_set) {
@@ -123,12 +124,12 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const int tiles = ((M + 255) / 256) * ((N + kG2BlockN - 1) / kG2BlockN);
+    const int tiles = ((M + 255) / 256) * ((N + kG2BlockN - 1) / kG2BlockN) * ksplit;
     int clusters = g_num_sms / 2;
     if (tiles < clusters) clusters = tiles;
     static const int split_env = env_int("LFM_GEMM_SPLIT", 1);
     kern<<<2 * clusters, kG2Threads, kG2SmemBytes, s>>>(ta, tb, tout, tbh != nullptr ? *tbh : tb, M, N, K, ep, cg,
-                                                        (tbh != nullptr && split_env) ? 1 : 0);
+                                                        (tbh != nullptr && split_env) ? 1 : 0, ksplit, split_row_pitch);
     return cudaGetLastError();
 }
 

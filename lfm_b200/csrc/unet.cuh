@@ -329,6 +329,25 @@ attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     }
 }
 
+// Split-K epilogue: out[m, n] (+)= bias[n] + sum_s partial[s][m][n], slabs added in a fixed order (deterministic).
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, size_t slab /*elements*/, const float* __restrict__ bias,
+                                     float* __restrict__ out, int N, size_t n4, int accumulate) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + (i % (N / 4)));
+    float4 acc = b4;
+    for (int s = 0; s < S; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(partial + s * slab + i * 4);
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    float4* op = reinterpret_cast<float4*>(out) + i;
+    if (accumulate) {
+        const float4 o = *op;
+        acc.x += o.x, acc.y += o.y, acc.z += o.z, acc.w += o.w;
+    }
+    *op = acc;
+}
+
 // conv weight repack: [Cout, Cin, 3, 3] fp32 -> [Cout, 3, 3, Cin] bf16 (K index = (r*3+s)*Cin + c, K-major rows)
 __global__ void conv_weight_repack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps) {
     const size_t n = static_cast<size_t>(Cout) * Cin * taps;
