@@ -124,7 +124,7 @@ int64_t lfm_launch_count(const lfm_ctx* ctx);
  * a, w: bf16 device pointers.  block_n: 128 / 256 (one CTA per tile) or 512 (CTA-pair kernel, 256 x 256 tile). */
 int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float* bias, void* out, const float* gate,
                  int gate_stride, int rows_per_sample, int M, int N, int K, int epi, int block_n, void* stream);
-/* softmax(q k^T / 8) v on a [B*256, 3*D] bf16 qkv buffer -> out [B*256, D] bf16.  variant: 2 = persistent kernel (default), 0 = P in TMEM,
+/* softmax(q k^T / 8) v on a [B*256, 3*D] bf16 qkv buffer -> out [B*256, D] bf16.  variant: 3 = persistent single-TMEM-read kernel (default), 2 = persistent two-pass, 0 = P in TMEM,
  * 1 = P through shared memory.  dbg_s (optional) receives the raw S = q k^T as fp32 [B, H, 256, 256]. */
 int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, int H, int variant, float* dbg_s, void* stream);
 /* Intermediate activations of the last lfm_forward (fp32 token stream [B*T, D] after all blocks). */

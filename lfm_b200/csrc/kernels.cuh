@@ -75,7 +75,7 @@ skinny_linear_kernel(const float* __restrict__ W, const float* __restrict__ bias
 // reference models/DiT.py:279-280).  p = 2, C = 4 => patch vector (c, p, q) of 16 floats.
 // One block = 8 tokens; thread d handles features d, d+256, ...
 __global__ void __launch_bounds__(256)
-patch_embed_kernel(const float* __restrict__ x, int x_rows, const float* __restrict__ W /*[D,16]*/,
+patch_embed_kernel(const float* __restrict__ x, int x_rows, const float* __restrict__ Wt /*[16,D] (transposed at upload)*/,
                    const float* __restrict__ bias, const float* __restrict__ pos /*[T,D]*/, float* __restrict__ tok,
                    int D, int G /*grid side*/, int C, int M) {
     __shared__ float patch[8][16];
@@ -98,12 +98,10 @@ patch_embed_kernel(const float* __restrict__ x, int x_rows, const float* __restr
     for (int d4 = threadIdx.x; d4 < D / 4; d4 += 256) {
         float w[4][16];
 #pragma unroll
-        for (int f = 0; f < 4; ++f)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(4 * d4 + f) * 16) + v);
-                w[f][4 * v] = w4.x, w[f][4 * v + 1] = w4.y, w[f][4 * v + 2] = w4.z, w[f][4 * v + 3] = w4.w;
-            }
+        for (int e = 0; e < 16; ++e) {  // coalesced: consecutive threads read consecutive float4 of row e
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(Wt + static_cast<size_t>(e) * D) + d4);
+            w[0][e] = w4.x, w[1][e] = w4.y, w[2][e] = w4.z, w[3][e] = w4.w;
+        }
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + d4);
 #pragma unroll
         for (int tk = 0; tk < 8; ++tk) {
@@ -521,6 +519,14 @@ __global__ void axpy_kernel(const float* __restrict__ y, const float* __restrict
 __global__ void negate_kernel(float* __restrict__ v, size_t n) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) v[i] = -v[i];
+}
+
+// [rows, cols] fp32 -> [cols, rows] fp32 (patch-embed weight [D,16] -> [16,D])
+__global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<size_t>(rows) * cols) return;
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+    out[static_cast<size_t>(c) * rows + r] = in[i];
 }
 
 // fp32 -> bf16 weight repack (nn.Linear weights are already [N, K] K-major: a plain cast)

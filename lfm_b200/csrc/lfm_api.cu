@@ -14,6 +14,7 @@
 
 #include "attention.cuh"
 #include "attention2.cuh"
+#include "attention3.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -207,17 +208,23 @@ static cudaError_t launch_ln(cudaStream_t s, const float* x, __nv_bfloat16* y, c
     }
 }
 
-static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, const CUtensorMap& tout, int B, int H, int D) {
+static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, const CUtensorMap& tout, int B, int H, int D,
+                                     int variant = 2) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attention2_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(attention3_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
-    attention2_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
+    if (variant == 3)
+        attention3_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
+    else
+        attention2_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
     return cudaGetLastError();
 }
 
@@ -231,7 +238,8 @@ struct ParamSlot {
     std::vector<int64_t> shape;
     size_t numel = 0;
     bool to_bf16 = false;
-    int kind = 0;  // 0 copy fp32, 1 cast bf16, 2 conv [Co,Ci,kh,kw] -> bf16 [Co,kh,kw,Ci], 3 out-conv -> fp32 [4][9][C]
+    int kind = 0;  // 0 copy fp32, 1 cast bf16, 2 conv [Co,Ci,kh,kw] -> bf16 [Co,kh,kw,Ci], 3 out-conv -> fp32 [4][9][C],
+                   // 4 fp32 transpose [R, rest] -> [rest, R]
     bool set = false;
 };
 
@@ -366,7 +374,7 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     ctx->HW = desc->img_resolution;
     ctx->chw = ctx->C * ctx->HW * ctx->HW;
     ctx->Nmod = (6 * ctx->L + 2) * ctx->D;
-    ctx->attn_variant = env_int("LFM_ATTN_VARIANT", 2);
+    ctx->attn_variant = env_int("LFM_ATTN_VARIANT", 3);
     const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
 
     if (dev_alloc(ctx, &ctx->pos, (size_t)T * D)) return 1;
@@ -382,7 +390,7 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     if (dev_alloc(ctx, &ctx->w_mod, (size_t)ctx->Nmod * D)) return 1;
     if (dev_alloc(ctx, &ctx->b_mod, ctx->Nmod)) return 1;
     add_param(ctx, "pos_embed", ctx->pos, {1, T, D}, false);
-    add_param(ctx, "x_embedder.proj.weight", ctx->pe_w, {D, 4, 2, 2}, false);
+    add_param_kind(ctx, "x_embedder.proj.weight", ctx->pe_w, {D, 4, 2, 2}, 4);  // stored transposed [16, D]
     add_param(ctx, "x_embedder.proj.bias", ctx->pe_b, {D}, false);
     add_param(ctx, "t_embedder.mlp.0.weight", ctx->t_w0, {D, 256}, false);
     add_param(ctx, "t_embedder.mlp.0.bias", ctx->t_b0, {D}, false);
@@ -448,6 +456,10 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
             const int taps = static_cast<int>(s.shape[2] * s.shape[3]);
             conv_weight_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst),
                                                                    static_cast<int>(s.shape[0]), static_cast<int>(s.shape[1]), taps);
+        } else if (s.kind == 4) {
+            const int r0 = static_cast<int>(s.shape[0]);
+            transpose_f32_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<float*>(s.dst), r0,
+                                                              static_cast<int>(s.numel / r0));
         } else if (s.kind == 3) {
             conv_out_weight_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<float*>(s.dst),
                                                                        static_cast<int>(s.shape[1]));
@@ -601,8 +613,8 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
             CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv, &b.tmh_qkv));
             ctx->launches++;
         }
-        if (ctx->attn_variant == 2)
-            CUDA_OK(launch_attention2(s, ctx->tm_qkv_kv, ctx->tm_attn, rows, ctx->H, D));
+        if (ctx->attn_variant >= 2)
+            CUDA_OK(launch_attention2(s, ctx->tm_qkv_kv, ctx->tm_attn, rows, ctx->H, D, ctx->attn_variant));
         else if (ctx->attn_variant == 0)
             CUDA_OK(launch_attention_inst<true>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
         else
@@ -1159,7 +1171,7 @@ extern "C" int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, in
     if (!make_tmap_bf16(&tq, qkv_bf16, M, 3 * D, 128) || !make_tmap_bf16(&tkv, qkv_bf16, M, 3 * D, 256))
         return fail(ctx, "lfm_dbg_attention: tensor map encode failed");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (variant == 2) {
+    if (variant >= 2) {
         if (g_num_sms == 0) {
             int dev = 0;
             CUDA_OK(cudaGetDevice(&dev));
@@ -1169,7 +1181,7 @@ extern "C" int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, in
         }
         CUtensorMap tout;
         if (!make_tmap_bf16(&tout, out_bf16, M, D, 128)) return fail(ctx, "lfm_dbg_attention: tensor map encode failed");
-        CUDA_OK(launch_attention2(s, tkv, tout, B, H, D));
+        CUDA_OK(launch_attention2(s, tkv, tout, B, H, D, variant));
     } else if (variant == 0)
         CUDA_OK(launch_attention_inst<true>(s, tq, tkv, static_cast<__nv_bfloat16*>(out_bf16), B, H, D, dbg_s));
     else
