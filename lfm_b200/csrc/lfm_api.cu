@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "gemm4.cuh"
 #include "kernels.cuh"
 #include "unet.cuh"
 
@@ -134,13 +135,56 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
     return cudaGetLastError();
 }
 
-// block_n: 128 / 256 = one CTA per 128 x block_n tile; kGemmPair (512) = CTA pair per 256 x 256 tile
+// 4-CTA cluster kernel (two pairs sharing A by multicast; 256 x 512 block per cluster)
+template <int EPI>
+static cudaError_t launch_gemm4_inst(cudaStream_t s, const CUtensorMap& ta64, const CUtensorMap& tb, const CUtensorMap& tout,
+                                     int M, int N, int K, const GemmEpi& ep) {
+    static int max_clusters = -1;
+    auto kern = gemm4_bf16_tcgen05<EPI>;
+    if (max_clusters < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG4SmemBytes);
+        if (e != cudaSuccess) return e;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(4 * (g_num_sms / 4));
+        cfg.blockDim = dim3(kG4Threads);
+        cfg.dynamicSmemBytes = kG4SmemBytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 4;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int nc = 0;
+        e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+        if (e != cudaSuccess) return e;
+        max_clusters = nc > 0 ? nc : 1;
+        if (env_int("LFM_GEMM4_CLUSTERS", 0) > 0) max_clusters = env_int("LFM_GEMM4_CLUSTERS", 0);
+    }
+    const int n_blocks = (N + kG2BlockN - 1) / kG2BlockN;
+    const int items = ((M + 255) / 256) * ((n_blocks + 1) / 2);
+    const int clusters = items < max_clusters ? items : max_clusters;
+    kern<<<4 * clusters, kG4Threads, kG4SmemBytes, s>>>(ta64, tb, tout, M, N, K, ep);
+    return cudaGetLastError();
+}
+
+// block_n: 128 / 256 = one CTA per 128 x block_n tile; kGemmPair (512) = CTA pair per 256 x 256 tile;
+// kGemmQuad (1024) = cluster of two pairs per 256 x 512 block (A multicast)
 constexpr int kGemmPair = 512;
-static inline uint32_t weight_box_rows(int block_n) { return block_n == kGemmPair ? 128u : static_cast<uint32_t>(block_n); }
+constexpr int kGemmQuad = 1024;
+static inline uint32_t weight_box_rows(int block_n) { return (block_n == kGemmPair || block_n == kGemmQuad) ? 128u : static_cast<uint32_t>(block_n); }
 
 static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                                int epi, int block_n, const GemmEpi& ep, const CUtensorMap* tout = nullptr,
-                               const CUtensorMap* tbh = nullptr) {
+                               const CUtensorMap* tbh = nullptr, const CUtensorMap* ta64 = nullptr) {
+    if (block_n == kGemmQuad) {
+        if (tout == nullptr || ta64 == nullptr) return cudaErrorInvalidValue;
+        if (epi == EPI_BIAS_BF16) return launch_gemm4_inst<EPI_BIAS_BF16>(s, *ta64, tb, *tout, M, N, K, ep);
+        if (epi == EPI_BIAS_GELU_BF16) return launch_gemm4_inst<EPI_BIAS_GELU_BF16>(s, *ta64, tb, *tout, M, N, K, ep);
+        if (epi == EPI_GATE_RESID_F32) return launch_gemm4_inst<EPI_GATE_RESID_F32>(s, *ta64, tb, *tout, M, N, K, ep);
+        if (epi == EPI_BIAS_F32) return launch_gemm4_inst<EPI_BIAS_F32>(s, *ta64, tb, *tout, M, N, K, ep);
+        return cudaErrorInvalidValue;
+    }
     if (block_n == kGemmPair) {
         if (tout == nullptr) return cudaErrorInvalidValue;
         const ConvGeom cg{0, 0, 0, 0, 1};
@@ -282,6 +326,7 @@ struct lfm_ctx {
     __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hmid = nullptr, *c_silu = nullptr;
     CUtensorMap tm_xn, tm_attn, tm_hmid, tm_csilu, tm_qkv_q, tm_qkv_kv;
     CUtensorMap tmo_qkv, tmo_hmid, tmo_xtok;  // TMA-store epilogue targets
+    CUtensorMap tm64_xn, tm64_attn, tm64_hmid;  // box {64, 64}: quarter A slabs of the 4-CTA multicast kernel
 
     // solver state
     cudaStream_t stream = nullptr;
@@ -476,7 +521,7 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
 
 static int pick_bn(int N, const char* env, int dflt) {
     int bn = env_int(env, dflt);
-    if (bn != 128 && bn != 256 && bn != kGemmPair) bn = dflt;
+    if (bn != 128 && bn != 256 && bn != kGemmPair && bn != kGemmQuad) bn = dflt;
     return bn;
 }
 
@@ -547,6 +592,9 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
     ok &= make_tmap_bf16(&ctx->tm_qkv_q, ctx->qkv, M, 3 * D, 128);
     ok &= make_tmap_bf16(&ctx->tm_qkv_kv, ctx->qkv, M, 3 * D, 256);
     ok &= make_tmap_bf16(&ctx->tm_wmod, ctx->w_mod, ctx->Nmod, D, ctx->bn_mod);
+    ok &= make_tmap_bf16(&ctx->tm64_xn, ctx->xn, M, D, 64);
+    ok &= make_tmap_bf16(&ctx->tm64_attn, ctx->attn, M, D, 64);
+    ok &= make_tmap_bf16(&ctx->tm64_hmid, ctx->hmid, M, Hd, 64);
     ok &= make_tmap_out(&ctx->tmo_qkv, ctx->qkv, M, 3 * D, false);
     ok &= make_tmap_out(&ctx->tmo_hmid, ctx->hmid, M, Hd, false);
     ok &= make_tmap_out(&ctx->tmo_xtok, ctx->x_tok, M, D, true);
@@ -610,7 +658,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         ctx->launches++;
         {
             GemmEpi ep{b.b_qkv, ctx->qkv, 3 * D, nullptr, 0, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv, &b.tmh_qkv));
+            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv, &b.tmh_qkv, &ctx->tm64_xn));
             ctx->launches++;
         }
         if (ctx->attn_variant >= 2)
@@ -622,19 +670,19 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         ctx->launches++;
         {
             GemmEpi ep{b.b_proj, ctx->x_tok, D, mb + 2 * D, Nmod, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok, &b.tmh_proj));
+            CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok, &b.tmh_proj, &ctx->tm64_attn));
             ctx->launches++;
         }
         CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D));
         ctx->launches++;
         {
             GemmEpi ep{b.b_fc1, ctx->hmid, Hd, nullptr, 0, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_fc1, M, Hd, D, EPI_BIAS_GELU_BF16, ctx->bn_fc1, ep, &ctx->tmo_hmid, &b.tmh_fc1));
+            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_fc1, M, Hd, D, EPI_BIAS_GELU_BF16, ctx->bn_fc1, ep, &ctx->tmo_hmid, &b.tmh_fc1, &ctx->tm64_xn));
             ctx->launches++;
         }
         {
             GemmEpi ep{b.b_fc2, ctx->x_tok, D, mb + 5 * D, Nmod, T};
-            CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep, &ctx->tmo_xtok, &b.tmh_fc2));
+            CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep, &ctx->tmo_xtok, &b.tmh_fc2, &ctx->tm64_hmid));
             ctx->launches++;
         }
     }
@@ -1141,8 +1189,8 @@ extern "C" int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float*
                             void* stream) {
     lfm_ctx* ctx = nullptr;
     if (K % 64 != 0 || N % 8 != 0) return fail(ctx, "lfm_dbg_gemm: K must be a multiple of 64 and N of 8");
-    if (block_n != 128 && block_n != 256 && block_n != kGemmPair)
-        return fail(ctx, "lfm_dbg_gemm: block_n must be 128, 256 or 512 (CTA pair)");
+    if (block_n != 128 && block_n != 256 && block_n != kGemmPair && block_n != kGemmQuad)
+        return fail(ctx, "lfm_dbg_gemm: block_n must be 128, 256, 512 (CTA pair) or 1024 (4-CTA cluster)");
     if (g_num_sms == 0) {
         int dev = 0;
         CUDA_OK(cudaGetDevice(&dev));
@@ -1158,7 +1206,9 @@ extern "C" int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float*
     if (!make_tmap_out(&tout, out, M, N, epi >= 2)) return fail(ctx, "lfm_dbg_gemm: output tensor map encode failed");
     CUtensorMap tbh;
     if (!make_tmap_bf16(&tbh, w_bf16, N, K, 64)) return fail(ctx, "lfm_dbg_gemm: tensor map encode failed");
-    CUDA_OK(launch_gemm(static_cast<cudaStream_t>(stream), ta, tb, M, N, K, epi, block_n, ep, &tout, &tbh));
+    CUtensorMap ta64;
+    if (!make_tmap_bf16(&ta64, a_bf16, M, K, 64)) return fail(ctx, "lfm_dbg_gemm: tensor map encode failed");
+    CUDA_OK(launch_gemm(static_cast<cudaStream_t>(stream), ta, tb, M, N, K, epi, block_n, ep, &tout, &tbh, &ta64));
     return 0;
 }
 

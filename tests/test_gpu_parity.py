@@ -63,7 +63,10 @@ def make_big(model_type, dev, num_classes, label_dropout, max_batch):
 @pytest.mark.parametrize("M,N,K,epi,bn", [
     (128, 128, 64, 3, 128), (256, 512, 1024, 0, 256), (512, 1024, 1024, 1, 256), (512, 1024, 4096, 2, 256),
     (512, 1024, 4096, 2, 128), (64, 2048, 1024, 3, 256), (4, 1024, 256, 3, 256), (256, 1152, 384, 0, 256),
-    (256, 1152, 384, 1, 128), (16384, 3072, 1024, 0, 256), (16384, 1024, 1024, 2, 128)])
+    (256, 1152, 384, 1, 128), (16384, 3072, 1024, 0, 256), (16384, 1024, 1024, 2, 128),
+    # CTA-pair kernel (512) incl. tail splitting / N tails, and the 4-CTA multicast kernel (1024)
+    (256, 256, 64, 3, 512), (768, 1152, 384, 0, 512), (512, 1024, 4096, 2, 512), (16384, 1024, 4096, 2, 512),
+    (16384, 3072, 1024, 1, 512), (768, 768, 384, 1, 1024), (512, 1024, 4096, 2, 1024), (16384, 3072, 1024, 0, 1024)])
 def test_gemm_epilogues(dev, M, N, K, epi, bn):
     lib = _lib.load()
     g = torch.Generator().manual_seed(M + N + K + epi)

@@ -71,6 +71,15 @@ def group_gemm():
         gemm_case(M, N, K, epi, bn)
 
 
+def group_gemm4():
+    for (M, N, K, epi) in [(256, 512, 64, 3), (256, 512, 1024, 0), (512, 1024, 4096, 2), (768, 768, 384, 1), (16384, 3072, 1024, 0),
+                           (16384, 1024, 4096, 2), (16384, 4096, 1024, 1), (16384, 1024, 1024, 2)]:
+        gemm_case(M, N, K, epi, 1024)
+    for (N, K, epi) in ((3072, 1024, 0), (1024, 1024, 2), (4096, 1024, 1), (1024, 4096, 2)):
+        for bn in (1024, 512):
+            time_gemm(16384, N, K, epi, bn)
+
+
 def attn_ref(qkv, B, H):
     D = H * 64
     q, k, v = qkv.float().reshape(B, 256, 3, H, 64).permute(2, 0, 3, 1, 4)
@@ -281,5 +290,5 @@ if __name__ == "__main__":
     grp = sys.argv[1]
     print(f"=== {grp} ===", flush=True)
     t = time.time()
-    {"gemm": group_gemm, "attn": group_attn, "forward": group_forward, "sampler": group_sampler, "perf": group_perf, "unet": group_unet}[grp]()
+    {"gemm": group_gemm, "attn": group_attn, "forward": group_forward, "sampler": group_sampler, "perf": group_perf, "unet": group_unet, "gemm4": group_gemm4}[grp]()
     print(f"=== {grp} done in {time.time()-t:.1f}s ===", flush=True)
