@@ -408,14 +408,20 @@ __global__ void step_advance_kernel(StepState* st) {
 struct RkPtrs {
     const float* k[7];
 };
+struct RkCoef {   // passed by value as a kernel argument: no device upload, no host synchronisation
+    float c[8];
+};
+__global__ void set_scalar_kernel(float* dst, float v) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) dst[0] = v;
+}
 
 // y_out = y0 + sum_j (coef[j]) * k[j],  coef already multiplied by dt (fp32) on the host
-__global__ void rk_combine_kernel(const float* __restrict__ y0, RkPtrs kp, int nk, const float* __restrict__ coef,
+__global__ void rk_combine_kernel(const float* __restrict__ y0, RkPtrs kp, int nk, RkCoef coef,
                                   float* __restrict__ y_out, size_t n) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float acc = 0.f;
-    for (int j = 0; j < nk; ++j) acc = fmaf(kp.k[j][i], coef[j], acc);
+    for (int j = 0; j < nk; ++j) acc = fmaf(kp.k[j][i], coef.c[j], acc);
     y_out[i] = y0[i] + acc;
 }
 
@@ -424,7 +430,7 @@ __global__ void rk_combine_kernel(const float* __restrict__ y0, RkPtrs kp, int n
 constexpr int kRmsBlocks = 128;
 __global__ void __launch_bounds__(256)
 rms_ratio_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, RkPtrs kp,
-                         const float* __restrict__ coef, const float* __restrict__ y0, const float* __restrict__ y1,
+                         RkCoef coef, const float* __restrict__ y0, const float* __restrict__ y1,
                          float atol, float rtol, size_t n, double* __restrict__ partial) {
     __shared__ double wsum[8];
     double acc = 0.0;
@@ -435,7 +441,7 @@ rms_ratio_partial_kernel(const float* __restrict__ a, const float* __restrict__ 
             num = a[i] - (b != nullptr ? b[i] : 0.f);
         } else {
             num = 0.f;
-            for (int j = 0; j < 7; ++j) num = fmaf(kp.k[j][i], coef[j], num);
+            for (int j = 0; j < 7; ++j) num = fmaf(kp.k[j][i], coef.c[j], num);
         }
         const float tol = atol + rtol * fmaxf(fabsf(y0[i]), fabsf(y1[i]));
         const float r = num / tol;
@@ -462,12 +468,12 @@ __global__ void rms_finalize_kernel(const double* __restrict__ partial, int nblk
 
 // dense-output quartic of the last accepted step evaluated at x in [0,1] (torchdiffeq _interp_fit/_interp_evaluate)
 __global__ void dopri_interp_kernel(const float* __restrict__ y0, const float* __restrict__ y1, RkPtrs kp,
-                                    const float* __restrict__ coef_mid /*dt * c_mid*/, float dt, float xq,
+                                    RkCoef coef_mid /*dt * c_mid*/, float dt, float xq,
                                     float* __restrict__ out, size_t n) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float mid = 0.f;
-    for (int j = 0; j < 7; ++j) mid = fmaf(kp.k[j][i], coef_mid[j], mid);
+    for (int j = 0; j < 7; ++j) mid = fmaf(kp.k[j][i], coef_mid.c[j], mid);
     const float a0 = y0[i], a1 = y1[i], ym = a0 + mid, f0 = kp.k[0][i], f1 = kp.k[6][i];
     const float ca = 2.f * dt * (f1 - f0) - 8.f * (a1 + a0) + 16.f * ym;
     const float cb = dt * (5.f * f0 - 3.f * f1) + 18.f * a0 + 14.f * a1 - 32.f * ym;

@@ -996,8 +996,8 @@ struct Dopri {
 static int dp_func(Dopri& d, float s_time, const float* yv, float* k_out) {
     lfm_ctx* ctx = d.ctx;
     const float t = -s_time;
-    CUDA_OK(cudaMemcpyAsync(ctx->t_eval, &t, sizeof(float), cudaMemcpyHostToDevice, d.s));
-    CUDA_OK(cudaStreamSynchronize(d.s));  // &t is a stack variable
+    set_scalar_kernel<<<1, 32, 0, d.s>>>(ctx->t_eval, t);  // by-value launch argument: no host synchronisation
+    LAUNCH_OK();
     if (eval_velocity(ctx, d.s, ctx->t_eval, 1, yv, d.n_img, d.y, d.cfg_scale, k_out)) return 1;
     negate_kernel<<<blocks_for(d.n), 256, 0, d.s>>>(k_out, d.n);
     LAUNCH_OK();
@@ -1005,12 +1005,12 @@ static int dp_func(Dopri& d, float s_time, const float* yv, float* k_out) {
     return 0;
 }
 
-static int dp_rms(Dopri& d, const float* a, const float* b, const float* coef_dev, const float* y0, const float* y1,
+static int dp_rms(Dopri& d, const float* a, const float* b, const RkCoef& coef, const float* y0, const float* y1,
                   float atol, float rtol, float* out_host) {
     lfm_ctx* ctx = d.ctx;
     RkPtrs kp;
     for (int j = 0; j < 7; ++j) kp.k[j] = ctx->kbuf[j];
-    rms_ratio_partial_kernel<<<kRmsBlocks, 256, 0, d.s>>>(a, b, kp, coef_dev, y0, y1, atol, rtol, d.n, ctx->partial);
+    rms_ratio_partial_kernel<<<kRmsBlocks, 256, 0, d.s>>>(a, b, kp, coef, y0, y1, atol, rtol, d.n, ctx->partial);
     LAUNCH_OK();
     rms_finalize_kernel<<<1, 32, 0, d.s>>>(ctx->partial, kRmsBlocks, d.n, ctx->ratio);
     LAUNCH_OK();
@@ -1045,25 +1045,21 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
     const float atol_f = (float)atol, rtol_f = (float)rtol;
     RkPtrs kp;
     for (int j = 0; j < 7; ++j) kp.k[j] = k[j];
-    auto upload_coef = [&](const float* c, int cnt, int slot) -> int {
-        CUDA_OK(cudaMemcpyAsync(ctx->coef + slot * 8, c, cnt * sizeof(float), cudaMemcpyHostToDevice, s));
-        CUDA_OK(cudaStreamSynchronize(s));
-        return 0;
-    };
+    const RkCoef no_coef{};
 
     double s0 = -t0;
     const double s_end = -t1;
     // _before_integrate: f0 and the initial step (order 4 rule)
     if (dp_func(d, (float)s0, y0, k[0])) return 1;
     float d0, d1, d2;
-    if (dp_rms(d, y0, nullptr, nullptr, y0, y0, atol_f, rtol_f, &d0)) return 1;
-    if (dp_rms(d, k[0], nullptr, nullptr, y0, y0, atol_f, rtol_f, &d1)) return 1;
+    if (dp_rms(d, y0, nullptr, no_coef, y0, y0, atol_f, rtol_f, &d0)) return 1;
+    if (dp_rms(d, k[0], nullptr, no_coef, y0, y0, atol_f, rtol_f, &d1)) return 1;
     float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
     h0 = fabsf(h0);
     axpy_kernel<<<blocks_for(n), 256, 0, s>>>(y0, k[0], h0, ytmp, n);
     LAUNCH_OK();
     if (dp_func(d, (float)(s0 + (double)h0), ytmp, k[1])) return 1;
-    if (dp_rms(d, k[1], k[0], nullptr, y0, y0, atol_f, rtol_f, &d2)) return 1;
+    if (dp_rms(d, k[1], k[0], no_coef, y0, y0, atol_f, rtol_f, &d2)) return 1;
     d2 = fabsf(d2 / h0);
     float h1;
     if (d1 <= 1e-15f && d2 <= 1e-15f)
@@ -1083,11 +1079,10 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
         const double t0s = s_hi, t1s = t0s + dt;
         const float t0_32 = (float)t0s, dt_32 = (float)dt, t1_32 = (float)t1s;
         for (int i = 0; i < 6; ++i) {
-            float c[8];
-            for (int j = 0; j <= i; ++j) c[j] = (float)DP_BETA[i][j] * dt_32;
-            if (upload_coef(c, i + 1, 0)) return 1;
+            RkCoef cb{};
+            for (int j = 0; j <= i; ++j) cb.c[j] = (float)DP_BETA[i][j] * dt_32;
             float* yi = (i == 5) ? y1 : ytmp;
-            rk_combine_kernel<<<blocks_for(n), 256, 0, s>>>(y0, kp, i + 1, ctx->coef, yi, n);
+            rk_combine_kernel<<<blocks_for(n), 256, 0, s>>>(y0, kp, i + 1, cb, yi, n);
             LAUNCH_OK();
             float ti;
             if (DP_ALPHA[i] == 1.0)
@@ -1096,21 +1091,20 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
                 ti = t0_32 + (float)DP_ALPHA[i] * dt_32;
             if (dp_func(d, ti, yi, k[i + 1])) return 1;
         }
-        float c[8];
-        for (int j = 0; j < 7; ++j) c[j] = dt_32 * (float)DP_CERR[j];
-        if (upload_coef(c, 7, 1)) return 1;
+        RkCoef ce{};
+        for (int j = 0; j < 7; ++j) ce.c[j] = dt_32 * (float)DP_CERR[j];
         float ratio;
-        if (dp_rms(d, nullptr, nullptr, ctx->coef + 8, y0, y1, atol_f, rtol_f, &ratio)) return 1;
+        if (dp_rms(d, nullptr, nullptr, ce, y0, y1, atol_f, rtol_f, &ratio)) return 1;
         ratio = fabsf(ratio);
         const bool accept = ratio <= 1.0f;
         if (accept) {
             accepted++;
             if (t1s >= s_end) {
                 // last step: evaluate the quartic dense output at s_end and finish
-                for (int j = 0; j < 7; ++j) c[j] = dt_32 * (float)DP_MID[j];
-                if (upload_coef(c, 7, 2)) return 1;
+                RkCoef cm{};
+                for (int j = 0; j < 7; ++j) cm.c[j] = dt_32 * (float)DP_MID[j];
                 const float xq = (float)((s_end - t0s) / (t1s - t0s));
-                dopri_interp_kernel<<<blocks_for(n), 256, 0, s>>>(y0, y1, kp, ctx->coef + 16, dt_32, xq, ytmp, n);
+                dopri_interp_kernel<<<blocks_for(n), 256, 0, s>>>(y0, y1, kp, cm, dt_32, xq, ytmp, n);
                 LAUNCH_OK();
                 have_interp = true;
                 s_lo = t0s;
