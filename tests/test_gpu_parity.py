@@ -400,3 +400,50 @@ def test_unet_celeb512_full_size_properties(dev):
     traj, nfe = lfm_b200.sample_from_model(net, x, {}, args)
     s = net.last_stats
     assert int(nfe) == 2 + 6 * (s["accepted"] + s["rejected"]) and torch.isfinite(traj[-1]).all()
+
+
+# ------------------------------------------------------------------------------------------------ edges / CLI
+
+
+@pytest.mark.parametrize("B", [1, 3, 5])
+def test_odd_batch_sizes_and_ctx_growth(dev, B):
+    """Ragged sizes: token rows B*256 that are not a multiple of the 256-row pair tile per sample count, the native
+    context being re-created when a larger batch arrives, and the uniform-conditioning shortcut vs explicit vectors."""
+    g = load_golden("mini_cond")
+    cfg = cfg_from_golden(g)
+    sd = odit.synthetic_state_dict(cfg, int(g["weight_seed"]))
+    net = make_net(cfg, sd, dev)
+    gen = torch.Generator().manual_seed(100 + B)
+    x = torch.randn(B, 4, 32, 32, generator=gen)
+    y = torch.randint(0, cfg.num_classes, (B,), generator=gen)
+    t = torch.rand(B, generator=gen)
+    v = net(t.to(dev), x.to(dev), y.to(dev))
+    assert rel_l2(v.cpu(), odit.dit_forward(sd, cfg, t, x, y)) < TOL_NFE
+    # y=None + 0-d t (one shared conditioning row, stride-0 modulation table) == explicit null labels + [B] times
+    v0 = net(torch.tensor(0.37, device=dev), x.to(dev))
+    v1 = net(torch.full((B,), 0.37, device=dev), x.to(dev), torch.full((B,), cfg.table_rows - 1, device=dev))
+    assert rel_l2(v0.cpu(), v1.cpu()) < 1e-6
+    # a larger batch afterwards forces a bigger native context; results stay consistent
+    xb = torch.cat([x, x, x], 0).to(dev)
+    vb = net(torch.tensor(0.37, device=dev), xb)
+    assert rel_l2(vb[:B].cpu(), v0.cpu()) < 1e-6 and rel_l2(vb[2 * B:].cpu(), v0.cpu()) < 1e-6
+
+
+def test_cli_end_to_end(dev, tmp_path):
+    """The test_flow_latent.py-compatible CLI (R1/R4): synthetic weights, Karras Heun with CFG, latents saved."""
+    import numpy as np
+    from lfm_b200 import cli
+    out = str(tmp_path)
+    rc = cli.main(["--model_type", "DiT-B/2", "--image_size", "256", "--num_in_channels", "4", "--num_classes", "1000",
+                   "--label_dropout", "0.1", "--cfg_scale", "1.5", "--batch_size", "4", "--use_karras_samplers",
+                   "--method", "heun", "--num_steps", "4", "--synthetic_init", "3", "--n_sample", "16", "--no_decode",
+                   "--out_dir", out, "--device", "cuda:0"])
+    assert rc == 0
+    z = np.load(out + "/samples_cifar10_heun_4_cfg1.5_latents.npy")
+    assert z.shape == (4, 4, 32, 32) and np.isfinite(z).all() and np.abs(z).mean() > 0.1
+    # torchdiffeq-style entry + NFE counting mode
+    rc = cli.main(["--model_type", "DiT-B/2", "--image_size", "256", "--num_in_channels", "4", "--num_classes", "1",
+                   "--label_dropout", "0.", "--batch_size", "2", "--method", "euler", "--step_size", "0.25",
+                   "--synthetic_init", "3", "--n_sample", "8", "--no_decode", "--out_dir", out, "--device", "cuda:0",
+                   "--compute_nfe", "--measure_reps", "2"])
+    assert rc == 0
