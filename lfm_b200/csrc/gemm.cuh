@@ -29,7 +29,14 @@ struct GemmEpi {
     const float* gate;    // EPI_GATE_RESID_F32: gate[b * gate_stride + n]
     int gate_stride;      // elements between samples in the modulation table
     int rows_per_sample;  // tokens per sample (b = row / rows_per_sample)
+    // Optional (pair kernel, EPI_BIAS_F32): GroupNorm statistics of the OUTPUT accumulated in the epilogue -
+    // bins[(row / gn_hw) * 64 + 2 g + {0,1}] += {sum, sum of squares} of group g = column / gn_cpg, as 2^28 fixed point
+    // (integer atomics => the result does not depend on the order of arrival: deterministic).
+    unsigned long long* gn_bins = nullptr;
+    int gn_cpg = 0;
+    int gn_hw = 1;
 };
+constexpr double kGnFixScale = 268435456.0;  // 2^28
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;  // 64 bf16 = one 128-byte swizzle row

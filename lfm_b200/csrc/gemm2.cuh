@@ -147,6 +147,45 @@ LFM_DEVICE void epilogue_math(const uint32_t* v, float* f, const GemmEpi& ep, in
     }
 }
 
+// GroupNorm statistics of one 32-column chunk (see GemmEpi::gn_bins): per-thread sums over each group's columns,
+// warp reduction over the 32 rows, one 64-bit integer atomic per (group, moment).
+template <int CPG>
+LFM_DEVICE void gn_accumulate_chunk(const float* f, bool row_ok, int n0, unsigned long long* bins_b, int lane) {
+    constexpr int NG = CPG >= 32 ? 1 : 32 / CPG;   // groups inside this chunk
+    constexpr int W = CPG >= 32 ? 32 : CPG;        // columns per group inside this chunk
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const float v = row_ok ? f[gi * W + k] : 0.f;
+            s += v;
+            q = fmaf(v, v, q);
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        if (lane == 0) {
+            const int g = (n0 + gi * W) / CPG;
+            atomicAdd(bins_b + 2 * g, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(s) * kGnFixScale)));
+            atomicAdd(bins_b + 2 * g + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(q) * kGnFixScale)));
+        }
+    }
+}
+LFM_DEVICE void gn_accumulate(const float* f, const GemmEpi& ep, int row, int M, int n0, int N, int lane) {
+    if (n0 >= N) return;
+    unsigned long long* bins_b = ep.gn_bins + static_cast<size_t>((row < M ? row : M - 1) / ep.gn_hw) * 64;
+    bins_b = reinterpret_cast<unsigned long long*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(bins_b), 0));
+    const bool ok = row < M;
+    switch (ep.gn_cpg) {
+        case 4: gn_accumulate_chunk<4>(f, ok, n0, bins_b, lane); break;
+        case 8: gn_accumulate_chunk<8>(f, ok, n0, bins_b, lane); break;
+        case 16: gn_accumulate_chunk<16>(f, ok, n0, bins_b, lane); break;
+        case 32: gn_accumulate_chunk<32>(f, ok, n0, bins_b, lane); break;
+        case 64: gn_accumulate_chunk<64>(f, ok, n0, bins_b, lane); break;
+        default: break;
+    }
+}
+
 // Write this lane's row segment (128 bytes = 8 x 16 B) into the warp's 32-row staging tile, 128B-swizzled
 // (16-byte chunk j of row r lives at chunk j ^ (r & 7)): conflict-free, and the layout TMA expects.
 LFM_DEVICE void stage_row_f32(uint8_t* stg, int lane, const float* f) {
@@ -365,6 +404,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 tmem_ld_wait();
                 tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
                 epilogue_math<EPI>(va, f, ep, nbase + c * 32, N, gate_row);
+                if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + c * 32, N, lane);
                 // this staging tile is free once all but the most recent TMA op of this warp have READ their tile
                 uint8_t* stg = stg0 + sbuf * 4096;
                 if (lane == 0) tma_store_wait_read<0>();
@@ -386,6 +426,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 tmem_ld_wait();
                 if (c + 2 < nch) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
                 epilogue_math<EPI>(vb, f, ep, nbase + (c + 1) * 32, N, gate_row);
+                if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + (c + 1) * 32, N, lane);
                 if (kBf16Out) {
                     stage_row_bf16_half(stg, lane, f, 1);
                     fence_proxy_async();

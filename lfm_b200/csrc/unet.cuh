@@ -85,6 +85,7 @@ struct GnApplyArgs {
     Src2 src;
     int HW, C, nchunk;
     const double* partial;
+    const unsigned long long* bins;  // nullptr, or fixed-point {sum, sumsq} per (sample, group) from the producing conv
     const float* gamma;
     const float* beta;
     const float* film;  // nullptr, or per-sample [scale(C) | shift(C)] at film + b * film_stride
@@ -105,9 +106,14 @@ gn_apply_kernel(GnApplyArgs a) {
     const int b = blockIdx.y;
     if (threadIdx.x < 32) {
         double S = 0.0, Q = 0.0;
-        for (int c = 0; c < a.nchunk; ++c) {  // fixed order => deterministic
-            S += a.partial[(static_cast<size_t>(b) * a.nchunk + c) * 64 + 2 * threadIdx.x];
-            Q += a.partial[(static_cast<size_t>(b) * a.nchunk + c) * 64 + 2 * threadIdx.x + 1];
+        if (a.bins != nullptr) {  // statistics accumulated by the producing convolution's epilogue (integer, order-free)
+            S = static_cast<double>(static_cast<long long>(a.bins[static_cast<size_t>(b) * 64 + 2 * threadIdx.x])) / 268435456.0;
+            Q = static_cast<double>(static_cast<long long>(a.bins[static_cast<size_t>(b) * 64 + 2 * threadIdx.x + 1])) / 268435456.0;
+        } else {
+            for (int c = 0; c < a.nchunk; ++c) {  // fixed order => deterministic
+                S += a.partial[(static_cast<size_t>(b) * a.nchunk + c) * 64 + 2 * threadIdx.x];
+                Q += a.partial[(static_cast<size_t>(b) * a.nchunk + c) * 64 + 2 * threadIdx.x + 1];
+            }
         }
         const double n = static_cast<double>(a.HW) * cpg;
         const double mean = S / n;
@@ -346,6 +352,77 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, s
         acc.x += o.x, acc.y += o.y, acc.z += o.z, acc.w += o.w;
     }
     *op = acc;
+}
+
+// Same computation with K and V of the (sample, head) staged ONCE in shared memory (rows padded by 16 bytes so the
+// 16-byte per-lane key reads are bank-conflict free); 8 warps share them, one query per warp at a time.
+// Used when (2 T ch + pad) bf16 fit in shared memory (all LFM presets: T <= 64, ch <= 256).
+__global__ void __launch_bounds__(256)
+attention_small_smem_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int C, int heads) {
+    extern __shared__ __align__(16) uint8_t s_kv[];
+    __shared__ float s_q[8][256];
+    __shared__ float s_p[8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / heads, head = blockIdx.x % heads;
+    const int ch = C / heads;
+    const int rs = ch * 2 + 16;  // padded row stride in bytes
+    uint8_t* sK = s_kv;
+    uint8_t* sV = s_kv + static_cast<size_t>(T) * rs;
+    const size_t ld = static_cast<size_t>(3) * C;
+    const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * T * ld + static_cast<size_t>(head) * 3 * ch;
+    const int cpr = ch / 8;  // 16-byte chunks per row
+    for (int i = threadIdx.x; i < T * cpr; i += 256) {
+        const int s = i / cpr, c = (i % cpr) * 8;
+        *reinterpret_cast<uint4*>(sK + s * rs + c * 2) = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(s) * ld + ch + c);
+        *reinterpret_cast<uint4*>(sV + s * rs + c * 2) = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(s) * ld + 2 * ch + c);
+    }
+    __syncthreads();
+    const float scale2 = rsqrtf(static_cast<float>(ch));
+    for (int t = warp; t < T; t += 8) {
+        for (int c = lane; c < ch; c += 32) s_q[warp][c] = __bfloat162float(base[static_cast<size_t>(t) * ld + c]);
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int s = lane; s < T; s += 32) {
+            const uint8_t* kp = sK + s * rs;
+            float acc = 0.f;
+            for (int c = 0; c < ch; c += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(kp + c * 2);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __bfloat1622float2(h2[k]);
+                    acc = fmaf(s_q[warp][c + 2 * k], f.x, acc);
+                    acc = fmaf(s_q[warp][c + 2 * k + 1], f.y, acc);
+                }
+            }
+            acc *= scale2;
+            s_p[warp][s] = acc;
+            mx = fmaxf(mx, acc);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int s = lane; s < T; s += 32) {
+            const float p = __expf(s_p[warp][s] - mx);
+            s_p[warp][s] = p;
+            sum += p;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        const float inv = 1.f / sum;
+        for (int c0 = 2 * lane; c0 < ch; c0 += 64) {
+            float a0 = 0.f, a1 = 0.f;
+            const uint8_t* vp = sV + c0 * 2;
+#pragma unroll 4
+            for (int s = 0; s < T; ++s) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vp + s * rs));
+                const float p = s_p[warp][s];
+                a0 = fmaf(p, f.x, a0);
+                a1 = fmaf(p, f.y, a1);
+            }
+            *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * T + t) * C + head * ch + c0) = pack_bf16x2(a0 * inv, a1 * inv);
+        }
+        __syncwarp();
+    }
 }
 
 // conv weight repack: [Cout, Cin, 3, 3] fp32 -> [Cout, 3, 3, Cin] bf16 (K index = (r*3+s)*Cin + c, K-major rows)
