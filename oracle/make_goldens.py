@@ -133,10 +133,73 @@ def make_unet_goldens(g):
     print("wrote unet_celeb256", len(sd), "tensors")
 
 
+EDM_CASES = {
+    # DhariwalUNet (models/EDM.py) with the preset topology rules; channel counts are multiples of 128
+    "edm_mini": (dict(img_resolution=16, label_dim=0, model_channels=128, channel_mult=(1, 2), num_blocks=1,
+                      attn_resolutions=(8,)), 31, 2),
+    "edm_mini_cond": (dict(img_resolution=32, label_dim=10, model_channels=128, channel_mult=(1, 2, 3), num_blocks=2,
+                           attn_resolutions=(16, 8)), 32, 3),
+    # the ffhq_adm / bed_adm preset at full width (test_args/ffhq_adm.txt: nf 256, ch_mult 1 2 3 4, attn 16 8 4)
+    "edm_ffhq": (dict(img_resolution=32, label_dim=0, model_channels=256, channel_mult=(1, 2, 3, 4), num_blocks=2,
+                      attn_resolutions=(16, 8, 4)), 1, 1),
+}
+
+
+def make_edm_goldens(g):
+    """DhariwalUNet fixtures from the reference's own module (models/EDM.py:716-861)."""
+    from models.EDM import DhariwalUNet
+    from oracle import edm as oedm
+
+    for name, (kw, seed, B) in EDM_CASES.items():
+        cfg = oedm.EDMConfig(**kw)
+        net = DhariwalUNet(img_resolution=kw["img_resolution"], in_channels=4, out_channels=4, label_dim=kw["label_dim"],
+                           augment_dim=0, model_channels=kw["model_channels"], channel_mult=list(kw["channel_mult"]),
+                           channel_mult_emb=4, num_blocks=kw["num_blocks"], attn_resolutions=list(kw["attn_resolutions"]),
+                           dropout=0.0, label_dropout=0.0)
+        ref_keys = list(net.state_dict().keys())
+        assert ref_keys == list(oedm.param_shapes(cfg).keys()), "state_dict key order differs from oracle.edm.param_shapes"
+        for k, v in net.state_dict().items():
+            if k.endswith("resample_filter"):
+                assert torch.all(v == 0.25) and tuple(v.shape) == (1, 1, 2, 2)
+        sd = oedm.synthetic_state_dict(cfg, seed)
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        S = kw["img_resolution"]
+        x = torch.randn(B, 4, S, S, generator=g)
+        tv = torch.tensor([0.85, 0.3, 0.55][:B])
+        t0 = torch.tensor(0.42)
+        out = {"x": x, "t_vec": tv, "t_scalar": t0, "weight_seed": np.int64(seed), "n_tensors": np.int64(len(sd)),
+               "cfg_img_resolution": np.int64(S), "cfg_label_dim": np.int64(kw["label_dim"]),
+               "cfg_model_channels": np.int64(kw["model_channels"]), "cfg_num_blocks": np.int64(kw["num_blocks"]),
+               "cfg_channel_mult": np.array(kw["channel_mult"], dtype=np.int64),
+               "cfg_attn_resolutions": np.array(kw["attn_resolutions"], dtype=np.int64)}
+        out["v_scalar"] = net(t0, x)
+        if kw["label_dim"]:
+            y = torch.randint(0, kw["label_dim"], (B,), generator=g)
+            out["y"] = y
+            out["v"] = net(tv, x, y)
+            # forward_with_cfg on the doubled batch; the second-half labels are dropped inside (drop_half_label), so
+            # they only need to be legal class ids for one_hot
+            x2 = torch.cat([x, x], 0)
+            y2 = torch.cat([y, torch.zeros(B, dtype=torch.long)], 0)
+            out["y_cfg"] = y2
+            out["t_cfg"] = torch.tensor([0.4] * (2 * B))
+            out["v_cfg_1p25"] = net.forward_with_cfg(out["t_cfg"], x2, y2, cfg_scale=1.25)
+        else:
+            out["v"] = net(tv, x)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
+        print("wrote", name, len(sd), "tensors, absmean(v)=%.4f" % float(out["v"].abs().mean()))
+        del net
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
     models, ks = _import_reference()
+    if sys.argv[1:] == ["edm"]:     # only the DhariwalUNet fixtures (own generator: the others stay byte-identical)
+        make_edm_goldens(torch.Generator().manual_seed(8765))
+        return
     g = torch.Generator().manual_seed(1234)
 
     for name, (kw, seed) in CASES.items():
@@ -199,6 +262,7 @@ def main():
         del net
 
     make_unet_goldens(torch.Generator().manual_seed(4321))
+    make_edm_goldens(torch.Generator().manual_seed(8765))
 
     # spot values of the fixed table quoted in SURVEY.md 8(c)
     pe = odit.pos_embed_2d(1024, 16)
