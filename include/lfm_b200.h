@@ -61,6 +61,22 @@ typedef struct lfm_unet_desc {
     int32_t num_classes;               /* 0: unconditional; > 0: label_emb rows (y is then required) */
 } lfm_unet_desc;
 
+/* Constructor arguments of the reference EDM-style ADM network DhariwalUNet (models/EDM.py:716-735 as called by
+ * get_edm_network, models/EDM.py:906-921, for `--model_type adm` without `--use_origin_adm`: the ffhq_adm / bed_adm /
+ * imnet_adm presets).  channel_mult_emb = 4, channels_per_head = 64, augment_dim = 0, use_context = False. */
+typedef struct lfm_edm_desc {
+    int32_t img_resolution;       /* latent side (config.image_size // config.f), e.g. 32 */
+    int32_t in_channels;          /* 4 */
+    int32_t out_channels;         /* 4 */
+    int32_t label_dim;            /* 0: unconditional; > 0: one-hot width of map_label */
+    int32_t model_channels;       /* nf, multiple of 128 */
+    int32_t n_mult;               /* number of entries used in channel_mult */
+    int32_t channel_mult[8];
+    int32_t num_blocks;           /* residual blocks per resolution (config.num_res_blocks) */
+    int32_t n_attn_res;           /* number of entries used in attn_resolutions */
+    int32_t attn_resolutions[8];  /* feature-map RESOLUTIONS with self-attention (EDM.py:788) */
+} lfm_edm_desc;
+
 typedef struct lfm_ode_stats {
     int64_t nfe;       /* network evaluations */
     int64_t accepted;  /* dopri5 accepted steps */
@@ -74,6 +90,15 @@ int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out);
  * lfm_set_param / lfm_finalize / lfm_forward / lfm_sample_* entry points then operate on the UNet
  * (model(t, x, y) = UNetModel.forward, unet.py:613-655; it has no forward_with_cfg: cfg_scale must be <= 1). */
 int lfm_create_unet(const lfm_unet_desc* desc, int device, lfm_ctx** out);
+
+/* models/__init__.py:10-11 create_network(config) -> get_edm_network(config) -> DhariwalUNet (EDM.py:906-921).
+ * The same lfm_set_param / lfm_finalize / lfm_forward / lfm_sample_* entry points then operate on it:
+ * model(t, x, y) = DhariwalUNet.forward (EDM.py:812-845; y may be NULL even for a class-conditional net: the label
+ * term is then skipped, :823) and cfg_scale > 1 = forward_with_cfg (EDM.py:847-861: the labels of the second half of
+ * the batch are DROPPED - pass label_dim there, or anything: rows [B/2, B) of y are ignored).
+ * State-dict keys as in the reference, including the constant `*.resample_filter` buffers of the up/down blocks
+ * (accepted and checked to be 0.25). */
+int lfm_create_edm(const lfm_edm_desc* desc, int device, lfm_ctx** out);
 
 /* nn.Module.load_state_dict (test_flow_latent.py:142): one call per state-dict entry, `key` exactly as in the
  * reference state_dict; `ptr` may be a host or a device pointer (fp32).  The data is copied

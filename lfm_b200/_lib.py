@@ -21,6 +21,13 @@ class UnetDesc(C.Structure):
                 ("num_heads", C.c_int32), ("num_head_channels", C.c_int32), ("num_classes", C.c_int32)]
 
 
+class EdmDesc(C.Structure):
+    _fields_ = [("img_resolution", C.c_int32), ("in_channels", C.c_int32), ("out_channels", C.c_int32),
+                ("label_dim", C.c_int32), ("model_channels", C.c_int32), ("n_mult", C.c_int32),
+                ("channel_mult", C.c_int32 * 8), ("num_blocks", C.c_int32), ("n_attn_res", C.c_int32),
+                ("attn_resolutions", C.c_int32 * 8)]
+
+
 class OdeStats(C.Structure):
     _fields_ = [("nfe", C.c_int64), ("accepted", C.c_int64), ("rejected", C.c_int64)]
 
@@ -30,6 +37,7 @@ _P = C.c_void_p
 SYMBOLS = {
     "lfm_create": (C.c_int, [C.POINTER(ModelDesc), C.c_int, C.POINTER(_P)]),
     "lfm_create_unet": (C.c_int, [C.POINTER(UnetDesc), C.c_int, C.POINTER(_P)]),
+    "lfm_create_edm": (C.c_int, [C.POINTER(EdmDesc), C.c_int, C.POINTER(_P)]),
     "lfm_set_param": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "lfm_finalize": (C.c_int, [_P, C.c_int]),
     "lfm_forward": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_float, _P, _P]),

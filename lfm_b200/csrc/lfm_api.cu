@@ -283,7 +283,9 @@ struct ParamSlot {
     size_t numel = 0;
     bool to_bf16 = false;
     int kind = 0;  // 0 copy fp32, 1 cast bf16, 2 conv [Co,Ci,kh,kw] -> bf16 [Co,kh,kw,Ci], 3 out-conv -> fp32 [4][9][C],
-                   // 4 fp32 transpose [R, rest] -> [rest, R]
+                   // 4 fp32 transpose [R, rest] -> [rest, R], 5 / 6 EDM qkv weight / bias row re-order (aux0 = head dim,
+                   // aux1 = target layout), 7 constant resample_filter (validated, not stored)
+    int aux0 = 0, aux1 = 0;
     bool set = false;
 };
 
@@ -379,6 +381,12 @@ static void add_param(lfm_ctx* ctx, const std::string& key, void* dst, std::vect
 static void add_param_kind(lfm_ctx* ctx, const std::string& key, void* dst, std::vector<int64_t> shape, int kind) {
     add_param(ctx, key, dst, shape, kind != 0);
     ctx->params[key].kind = kind;
+}
+
+static void add_param_aux(lfm_ctx* ctx, const std::string& key, void* dst, std::vector<int64_t> shape, int kind, int aux0, int aux1) {
+    add_param_kind(ctx, key, dst, shape, kind);
+    ctx->params[key].aux0 = aux0;
+    ctx->params[key].aux1 = aux1;
 }
 
 extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out) {
@@ -508,6 +516,17 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
         } else if (s.kind == 3) {
             conv_out_weight_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<float*>(s.dst),
                                                                        static_cast<int>(s.shape[1]));
+        } else if (s.kind == 5) {
+            edm_qkv_weight_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst),
+                                                                      static_cast<int>(s.shape[1]), s.aux0, s.aux1);
+        } else if (s.kind == 6) {
+            edm_qkv_bias_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<float*>(s.dst),
+                                                                    static_cast<int>(s.shape[0] / 3), s.aux0, s.aux1);
+        } else if (s.kind == 7) {
+            float h[4] = {0.f, 0.f, 0.f, 0.f};
+            CUDA_OK(cudaMemcpy(h, ctx->staging, sizeof(h), cudaMemcpyDeviceToHost));
+            for (float v : h)
+                if (v != 0.25f) return fail(ctx, "lfm_set_param(%s): resample_filter must be [[0.25, 0.25], [0.25, 0.25]] (EDM.py:96-98)", key);
         } else {
             f32_to_bf16_kernel<<<blocks_for((s.numel + 3) / 4), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst), s.numel);
         }
@@ -625,6 +644,8 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
 
 #include "unet_host.inc"
 
+static int ctx_unet_variant(const lfm_ctx* ctx) { return ctx->un != nullptr ? ctx->un->variant : 0; }
+
 static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_numel, const float* x, int x_rows,
                           const long long* y, int rows) {
     if (ctx->arch == LFM_ARCH_UNET) return launch_unet(ctx, s, t, t_numel, x, x_rows, y, rows);
@@ -709,7 +730,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
 static int eval_velocity(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_numel, const float* x, int n_img,
                          const long long* y, float cfg_scale, float* v_out) {
     const size_t n = (size_t)n_img * ctx->chw;
-    if (cfg_scale > 1.0f && ctx->arch == LFM_ARCH_UNET)
+    if (cfg_scale > 1.0f && ctx->arch == LFM_ARCH_UNET && ctx_unet_variant(ctx) == 0)
         return fail(ctx, "UNetModel has no forward_with_cfg (reference models/guided_diffusion/unet.py): cfg_scale must be <= 1");
     if (cfg_scale > 1.0f) {
         if (launch_network(ctx, s, t, t_numel, x, n_img, y, 2 * n_img)) return 1;
@@ -738,7 +759,7 @@ extern "C" int lfm_forward(lfm_ctx* ctx, const float* t, int t_numel, const floa
     CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long* yl = reinterpret_cast<const long long*>(y);
-    if (cfg_scale > 1.0f && ctx->arch == LFM_ARCH_UNET)
+    if (cfg_scale > 1.0f && ctx->arch == LFM_ARCH_UNET && ctx_unet_variant(ctx) == 0)
         return fail(ctx, "lfm_forward: UNetModel has no forward_with_cfg; cfg_scale must be <= 1");
     if (cfg_scale > 1.0f) {
         if (B % 2 != 0) return fail(ctx, "lfm_forward: forward_with_cfg needs an even batch (got %d)", B);

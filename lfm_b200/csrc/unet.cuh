@@ -425,6 +425,85 @@ attention_small_smem_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// EDM-style ADM (DhariwalUNet, reference models/EDM.py) additions.
+//
+// Resampling inside a UNetBlock (EDM.py:101-134 with resample_filter [1, 1]): `down` = 2x2 mean, `up` = nearest x2.
+// One launch moves BOTH tensors of the block to the new resolution: the GroupNorm+SiLU'd bf16 operand of conv0 and
+// the fp32 stream that becomes the (weight-free, kernel = 0) skip branch.  Index space = output pixels x C/4.
+template <bool UP>
+__global__ void resample2x_kernel(const __nv_bfloat16* __restrict__ a_in, __nv_bfloat16* __restrict__ a_out,
+                                  const float* __restrict__ x_in, float* __restrict__ x_out, int B, int H, int W, int C) {
+    const int Ho = UP ? 2 * H : H / 2, Wo = UP ? 2 * W : W / 2;
+    const size_t n4 = static_cast<size_t>(B) * Ho * Wo * (C / 4);
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int c = static_cast<int>(i % (C / 4)) * 4;
+    size_t r = i / (C / 4);
+    const int wo = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int ho = static_cast<int>(r % Ho);
+    const int b = static_cast<int>(r / Ho);
+    if (UP) {
+        const size_t src = ((static_cast<size_t>(b) * H + ho / 2) * W + wo / 2) * C + c;
+        *reinterpret_cast<uint2*>(a_out + i * 4) = *reinterpret_cast<const uint2*>(a_in + src);
+        *reinterpret_cast<float4*>(x_out + i * 4) = *reinterpret_cast<const float4*>(x_in + src);
+    } else {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), xs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const size_t src = ((static_cast<size_t>(b) * H + 2 * ho + dy) * W + 2 * wo + dx) * C + c;
+                const uint2 u = *reinterpret_cast<const uint2*>(a_in + src);
+                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+                acc.x += f0.x, acc.y += f0.y, acc.z += f1.x, acc.w += f1.y;
+                const float4 v = *reinterpret_cast<const float4*>(x_in + src);
+                xs.x += v.x, xs.y += v.y, xs.z += v.z, xs.w += v.w;
+            }
+        *reinterpret_cast<uint2*>(a_out + i * 4) =
+            make_uint2(pack_bf16x2(0.25f * acc.x, 0.25f * acc.y), pack_bf16x2(0.25f * acc.z, 0.25f * acc.w));
+        *reinterpret_cast<float4*>(x_out + i * 4) = make_float4(0.25f * xs.x, 0.25f * xs.y, 0.25f * xs.z, 0.25f * xs.w);
+    }
+}
+
+// UNetBlock.qkv rows (EDM.py:277-281: out-channel = head*3dh + c*3 + {q,k,v}) re-ordered at load time into the
+// layout of the attention kernel that will consume them:
+//   mode 0  head*3dh + {q,k,v}*dh + c   (attention_small*_kernel, the guided-diffusion "legacy" order)
+//   mode 1  {q,k,v}*C + head*dh + c     (attention3_t256_d64, the DiT order)
+LFM_DEVICE int edm_qkv_src_row(int r, int C, int dh, int mode) {
+    int h, w, c;
+    if (mode == 0) {
+        h = r / (3 * dh), w = (r % (3 * dh)) / dh, c = r % dh;
+    } else {
+        w = r / C, h = (r % C) / dh, c = r % dh;
+    }
+    return h * 3 * dh + c * 3 + w;
+}
+__global__ void edm_qkv_weight_repack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int dh, int mode) {
+    const size_t n = static_cast<size_t>(3) * C * C;
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = static_cast<int>(i / C), k = static_cast<int>(i % C);
+    out[i] = __float2bfloat16(w[static_cast<size_t>(edm_qkv_src_row(r, C, dh, mode)) * C + k]);
+}
+__global__ void edm_qkv_bias_repack_kernel(const float* __restrict__ b, float* __restrict__ out, int C, int dh, int mode) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= 3 * C) return;
+    out[r] = b[edm_qkv_src_row(r, C, dh, mode)];
+}
+
+// Labels of one network batch for the one-hot column gather of map_label (EDM.py:822-829): row b reads table row
+// y[b]; under forward_with_cfg (drop_half_label) rows >= rows/2 read the all-zero row `null_row`.
+__global__ void edm_labels_kernel(const long long* __restrict__ y, long long* __restrict__ out, int rows, int drop_from, int null_row) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= rows) return;
+    long long v = y[b];
+    if (b >= drop_from || v < 0 || v >= null_row) v = null_row;
+    out[b] = v;
+}
+
 // conv weight repack: [Cout, Cin, 3, 3] fp32 -> [Cout, 3, 3, Cin] bf16 (K index = (r*3+s)*Cin + c, K-major rows)
 __global__ void conv_weight_repack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps) {
     const size_t n = static_cast<size_t>(Cout) * Cin * taps;

@@ -235,11 +235,13 @@ DiT_models = {
 
 
 def create_network(config):
-    """reference models/__init__.py:6-17.  ADM / EDM networks are not part of this build yet."""
+    """reference models/__init__.py:6-17: UNetModel (--use_origin_adm), the EDM family (model_type without "DiT":
+    only "adm" = DhariwalUNet is native) or a DiT."""
     if getattr(config, "use_origin_adm", False):
         return get_flow_model(config)
     if "DiT" not in config.model_type:
-        raise NotImplementedError("EDM networks (models/EDM.py) are outside the B200 hot path (SURVEY.md 8(f))")
+        from .edm import get_edm_network
+        return get_edm_network(config)
     return DiT_models[config.model_type](
         img_resolution=config.image_size // config.f,
         in_channels=config.num_in_channels,

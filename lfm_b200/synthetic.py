@@ -54,3 +54,24 @@ def synthetic_unet_state_dict(net, seed: int = 1) -> "dict[str, torch.Tensor]":
             fan_in = int(math.prod(shp[1:]))
             sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
     return sd
+
+
+def synthetic_edm_state_dict(net, seed: int = 1) -> "dict[str, torch.Tensor]":
+    """Same idea for the EDM-style DhariwalUNet (conv1 / proj / out_conv are zero-initialised, EDM.py:742): conv /
+    linear U(-a, a) with a = 1/sqrt(fan_in); GroupNorm weight 1 + 0.1 N, bias 0.1 N; biases and map_label 0.02 N;
+    resample_filter buffers keep their only legal value 0.25."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, p in net.state_dict().items():
+        shp = tuple(p.shape)
+        leaf = k.rsplit(".", 2)[-2]
+        if k.endswith("resample_filter"):
+            sd[k] = torch.full(shp, 0.25)
+        elif leaf.startswith("norm") or leaf == "out_norm":
+            sd[k] = (1.0 + 0.1 * torch.randn(shp, generator=g)) if k.endswith("weight") else 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith(".bias") or k == "map_label.weight":
+            sd[k] = 0.02 * torch.randn(shp, generator=g)
+        else:
+            fan_in = int(math.prod(shp[1:]))
+            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
+    return sd

@@ -402,6 +402,106 @@ def test_unet_celeb512_full_size_properties(dev):
     assert int(nfe) == 2 + 6 * (s["accepted"] + s["rejected"]) and torch.isfinite(traj[-1]).all()
 
 
+# ------------------------------------------------------------------------------------------------ EDM DhariwalUNet
+
+
+def make_edm(cfg, sd, dev, max_batch=None):
+    net = lfm_b200.DhariwalUNet(img_resolution=cfg.img_resolution, in_channels=4, out_channels=4, label_dim=cfg.label_dim,
+                                model_channels=cfg.model_channels, channel_mult=cfg.channel_mult, num_blocks=cfg.num_blocks,
+                                attn_resolutions=cfg.attn_resolutions, dropout=0.0, max_batch=max_batch)
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev).eval()
+
+
+@pytest.mark.parametrize("name", ["edm_mini", "edm_mini_cond", "edm_ffhq"])
+def test_edm_forward_vs_reference_fixture(dev, name):
+    """DhariwalUNet (models/EDM.py) through lfm_create_edm vs outputs of the reference's own module: vector and 0-d t,
+    labels, forward_with_cfg (drop_half_label), both attention kernels (256-token tcgen05 / short-grid SIMT), the
+    resampling blocks and the 56-channel groups of the 1792-wide concatenation (edm_ffhq)."""
+    from oracle import edm as oedm
+    from tests.test_oracle_edm import edm_cfg_from_golden
+    g = load_golden(name)
+    cfg = edm_cfg_from_golden(g)
+    net = make_edm(cfg, oedm.synthetic_state_dict(cfg, int(g["weight_seed"])), dev)
+    x = T(g["x"]).to(dev)
+    y = T(g["y"]).to(dev) if "y" in g else None
+    v = net(T(g["t_vec"]).to(dev), x, y)
+    assert rel_l2(v.cpu(), g["v"]) < TOL_UNET_NFE
+    assert torch.equal(v, net(T(g["t_vec"]).to(dev), x, y))            # deterministic
+    assert rel_l2(net(T(g["t_scalar"]).to(dev), x).cpu(), g["v_scalar"]) < TOL_UNET_NFE   # 0-d t, y = None
+    v1 = net(T(g["t_vec"])[:1].to(dev), x[:1], y[:1] if y is not None else None)
+    assert rel_l2(v1.cpu(), v[:1].cpu()) < 1e-5
+    if y is None:
+        # without map_label a y argument is ignored (EDM.py:823)
+        assert torch.equal(net(T(g["t_vec"]).to(dev), x, torch.zeros(x.shape[0], dtype=torch.long, device=dev)), v)
+    else:
+        x2 = torch.cat([x, x], 0)
+        vc = net.forward_with_cfg(T(g["t_cfg"]).to(dev), x2, T(g["y_cfg"]).to(dev), cfg_scale=1.25)
+        assert rel_l2(vc.cpu(), g["v_cfg_1p25"]) < TOL_UNET_NFE
+        n = x.shape[0]
+        assert torch.equal(vc[:n], vc[n:])
+        # the labels of the second half are dropped whatever they are
+        y_other = torch.cat([T(g["y_cfg"])[:n], torch.full((n,), cfg.label_dim - 1)]).to(dev)
+        assert torch.equal(net.forward_with_cfg(T(g["t_cfg"]).to(dev), x2, y_other, cfg_scale=1.25), vc)
+        with pytest.raises(RuntimeError):
+            net(0.5, x, torch.full((n,), cfg.label_dim, device=dev))   # one_hot rejects class ids >= label_dim
+
+
+def test_edm_solvers_vs_oracle(dev):
+    """The solver entry points on a DhariwalUNet: Karras Heun with CFG (imnet_adm style: y_null = zeros, CFG 1.25),
+    torchdiffeq-grid Euler and dopri5."""
+    from oracle import edm as oedm
+    from tests.test_oracle_edm import edm_cfg_from_golden
+    g = load_golden("edm_mini_cond")
+    cfg = edm_cfg_from_golden(g)
+    sd = oedm.synthetic_state_dict(cfg, int(g["weight_seed"]))
+    net = make_edm(cfg, sd, dev)
+    x = T(g["x"])[:2]
+    y = T(g["y"])[:2]
+    y2 = torch.cat([y, torch.zeros_like(y)])
+    fc = lambda tt, xx: oedm.edm_forward_with_cfg(sd, cfg, tt, xx, y2, 1.25)  # noqa: E731
+    out = lfm_b200.karras_sample(net, torch.cat([x, x]).to(dev), 4, clip_denoised=False, sigma_min=1e-5, sigma_max=1.0,
+                                 sampler="heun", model_kwargs=dict(y=y2.to(dev), cfg_scale=1.25))
+    assert rel_l2(out.cpu(), osol.karras_sample(fc, torch.cat([x, x]), 4, "heun")) < TOL_UNET_NFE
+    assert net.last_stats["nfe"] == 6 and torch.equal(out[:2], out[2:])
+    f = lambda tt, xx: oedm.edm_forward(sd, cfg, tt, xx, y)  # noqa: E731
+    args = types.SimpleNamespace(method="euler", step_size=0.25, perturb=False, cfg_scale=1.0, compute_nfe=False)
+    traj = lfm_b200.sample_from_model(net, x.to(dev), dict(y=y.to(dev)), args)
+    assert rel_l2(traj[-1].cpu(), osol.tdq_euler(f, x, 0.25)[0]) < TOL_UNET_NFE
+    args = types.SimpleNamespace(method="dopri5", atol=1e-2, rtol=1e-2, cfg_scale=1.0, compute_nfe=True)
+    traj, nfe = lfm_b200.sample_from_model(net, x.to(dev), dict(y=y.to(dev)), args)
+    ref, st = osol.tdq_dopri5(f, x, rtol=1e-2, atol=1e-2)
+    assert rel_l2(traj[-1].cpu(), ref) < TOL_UNET_NFE
+    assert abs(int(nfe) - st.nfe) <= 6 and int(nfe) == 2 + 6 * (net.last_stats["accepted"] + net.last_stats["rejected"])
+
+
+def test_edm_imnet_preset_full_size_properties(dev):
+    """The imnet_adm preset (test_args/imnet_adm.txt: nf 256, ch_mult 1 2 3 4, attention at 16 / 8 / 4, 1000 classes)
+    at batch 8: finiteness, batch independence, CFG halves, one oracle spot check."""
+    from lfm_b200.synthetic import synthetic_edm_state_dict
+    from oracle import edm as oedm
+    with torch.device("meta"):
+        net = lfm_b200.DhariwalUNet(img_resolution=32, in_channels=4, out_channels=4, label_dim=1000, model_channels=256,
+                                    channel_mult=(1, 2, 3, 4), num_blocks=2, attn_resolutions=(16, 8, 4), max_batch=16)
+    sd = synthetic_edm_state_dict(net, 1)
+    net = net.to_empty(device="cpu")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(8, 4, 32, 32, generator=g)
+    y = torch.randint(0, 1000, (8,), generator=g)
+    v = net(torch.tensor(0.5, device=dev), x.to(dev), y.to(dev))
+    assert torch.isfinite(v).all() and float(v.abs().mean()) > 1e-2
+    assert rel_l2(net(0.5, x[2:5].to(dev), y[2:5].to(dev)).cpu(), v[2:5].cpu()) < 1e-5
+    cfg = oedm.EDMConfig(label_dim=1000)
+    ref = oedm.edm_forward(sd, cfg, torch.tensor(0.5), x[:1], y[:1])
+    assert rel_l2(v[:1].cpu(), ref) < TOL_UNET_NFE
+    vc = net.forward_with_cfg(torch.tensor(0.5, device=dev), torch.cat([x, x]).to(dev), torch.cat([y, torch.zeros_like(y)]).to(dev),
+                              cfg_scale=1.25)
+    vu = net(torch.tensor(0.5, device=dev), x.to(dev))                   # y = None: the label term is skipped
+    assert rel_l2(vc[:8].cpu(), (vu + 1.25 * (v - vu)).cpu()) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ edges / CLI
 
 

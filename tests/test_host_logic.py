@@ -76,7 +76,7 @@ def test_no_cpu_path():
     with pytest.raises(NotImplementedError):
         lfm_b200.karras_sample(net, x, 4, clip_denoised=True, sampler="euler")
     with pytest.raises(NotImplementedError):
-        lfm_b200.create_network(types.SimpleNamespace(use_origin_adm=False, model_type="adm"))   # EDM nets
+        lfm_b200.create_network(types.SimpleNamespace(use_origin_adm=False, model_type="ddpm++"))   # SongUNet
 
 
 def test_create_network_factory():
@@ -148,3 +148,36 @@ def test_unet_state_dict_surface_and_factory():
     ref = ounet.synthetic_state_dict(ounet.UNetConfig(image_size=32, model_channels=128, num_res_blocks=1,
                                                       attention_resolutions=(2,), channel_mult=(1, 2), num_heads=2), 21)
     assert all(torch.equal(sd[k], ref[k]) for k in ref)
+
+
+def test_edm_state_dict_surface_and_factory():
+    """create_network -> get_edm_network -> DhariwalUNet (models/__init__.py:10-11, EDM.py:906-921): key set, order and
+    shapes of the ffhq_adm / imnet_adm presets, incl. the constant resample_filter buffers; init and error behaviour."""
+    from oracle import edm as oedm
+    cfg = types.SimpleNamespace(use_origin_adm=False, model_type="adm", image_size=256, f=8, num_in_channels=4,
+                                num_out_channels=4, label_dim=1000, nf=256, ch_mult=(1, 2, 3, 4), num_res_blocks=2,
+                                attn_resolutions=(16, 8, 4), dropout=0.1, label_dropout=0.1)
+    with torch.device("meta"):
+        net = lfm_b200.create_network(cfg)
+    want = oedm.param_shapes(oedm.EDMConfig(label_dim=1000))      # pinned to the reference by oracle/make_goldens.py
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert got == want and list(got) == list(want) and len(got) == 429
+    assert sum(k.endswith("resample_filter") for k in got) == 12   # 3 down + 3 up blocks, conv0 + skip each
+    cfg.model_type = "adm_context"
+    with pytest.raises(NotImplementedError):
+        lfm_b200.create_network(cfg)
+    small = lfm_b200.DhariwalUNet(img_resolution=16, in_channels=4, out_channels=4, label_dim=5, model_channels=128,
+                                  channel_mult=(1, 2), num_blocks=1, attn_resolutions=(8,))
+    # init_zero layers start at zero, resample filters at 0.25 (EDM.py:742,96-98)
+    assert float(small.out_conv.weight.abs().max()) == 0.0 and float(small.dec["8x8_in0"].proj.weight.abs().max()) == 0.0
+    assert torch.all(small.enc["8x8_down"].skip.resample_filter == 0.25)
+    from lfm_b200.synthetic import synthetic_edm_state_dict
+    sd = synthetic_edm_state_dict(small, 31)
+    ref = oedm.synthetic_state_dict(oedm.EDMConfig(img_resolution=16, label_dim=5, model_channels=128, channel_mult=(1, 2),
+                                                   num_blocks=1, attn_resolutions=(8,)), 31)
+    assert list(sd) == list(ref) and all(torch.equal(sd[k], ref[k]) for k in ref)
+    small.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError):                              # no CPU path
+        small(torch.tensor(0.5), torch.randn(2, 4, 16, 16))
+    with pytest.raises(RuntimeError):                              # one_hot semantics: class ids only
+        small(torch.tensor(0.5), torch.randn(2, 4, 16, 16), torch.tensor([0, 5]))

@@ -36,6 +36,8 @@ def test_struct_layouts():
     from lfm_b200 import _lib
     assert ctypes.sizeof(_lib.ModelDesc) == 9 * 4
     assert ctypes.sizeof(_lib.OdeStats) == 3 * 8
+    assert ctypes.sizeof(_lib.UnetDesc) == 26 * 4
+    assert ctypes.sizeof(_lib.EdmDesc) == 24 * 4
 
 
 def test_create_fails_loudly_without_gpu(lib):
