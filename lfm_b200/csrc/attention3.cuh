@@ -29,7 +29,7 @@ namespace lfm {
 __global__ void __launch_bounds__(kA2Threads, 1)
 attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D] bf16, box {64, 256}
                     const __grid_constant__ CUtensorMap tmap_out,  // out [M, D]  bf16, box {64, 128}
-                    int D, int H, int num_items, float scale_log2e) {
+                    int D, int H, int num_items, float scale_log2e, int reverse) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kA2StageBytes);
@@ -67,6 +67,8 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();
+    pdl_trigger();
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 8) {
@@ -75,7 +77,8 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
             int i = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++i) {
                 const int stage = i & 1;
-                const int b = item / H, h = item % H;
+                const int it = reverse ? num_items - 1 - item : item;  // last samples first: see GemmEpi::reverse_m
+                const int b = it / H, h = it % H;
                 uint8_t* st = smem + stage * kA2StageBytes;
                 mbar_wait(&empty[stage], ((i >> 1) & 1) ^ 1);
                 mbar_arrive_expect_tx(&full[stage], kA2StageBytes);
@@ -140,7 +143,8 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++i) {
             const int stage = i & 1;
             const uint32_t hp = i & 1;
-            const int b = item / H, h = item % H;
+            const int it = reverse ? num_items - 1 - item : item;
+            const int b = it / H, h = it % H;
             uint8_t* sO = smem + stage * kA2StageBytes + g * kAttnQBytes;  // Q_g's slot, reused for the output tile
             mbar_wait(&s_full[g], hp);
             tc_fence_after();

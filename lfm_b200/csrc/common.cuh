@@ -244,4 +244,11 @@ LFM_DEVICE float warp_max(float v) {
     return v;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor drains; it must not touch global memory the predecessor reads or writes before
+// pdl_wait() (which returns once ALL prerequisite grids have completed and flushed).  pdl_trigger() lets the NEXT
+// kernel in the stream begin launching.  Both are no-ops for ordinary launches.
+LFM_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+LFM_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace lfm

@@ -35,6 +35,9 @@ struct GemmEpi {
     unsigned long long* gn_bins = nullptr;
     int gn_cpg = 0;
     int gn_hw = 1;
+    // Pair kernel: walk the M blocks from the last to the first.  Consecutive kernels of a network alternate
+    // direction so that each one starts on the rows its producer touched LAST - the part still resident in L2.
+    int reverse_m = 0;
 };
 constexpr double kGnFixScale = 268435456.0;  // 2^28
 

@@ -263,6 +263,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
         }
         m_blk = tile / n_blocks;
         n_blk = tile % n_blocks;
+        if (ep.reverse_m) m_blk = m_blocks - 1 - m_blk;
     };
 
     if (warp == 0 && lane == 0) {
@@ -288,6 +289,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
     cluster_sync_all();  // barrier inits + TMEM allocation visible in both CTAs before any remote traffic
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // everything above overlapped the tail of the previous kernel; its outputs are complete from here on
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================

@@ -144,26 +144,36 @@ LFM_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, u
 template <int NV>  // NV = D / 128 float4 per lane
 __global__ void __launch_bounds__(256, 1)
 ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ shift,
-                   const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M) {
+                   const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M, int order) {
     constexpr int D = NV * 128;
     constexpr uint32_t kStageBytes = kLnRows * D * 4;
     extern __shared__ __align__(128) uint8_t ln_smem[];
     __shared__ __align__(8) uint64_t full_bar[kLnStages];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (M + kLnRows - 1) / kLnRows;
-    // contiguous tile range per block (keeps one block inside as few samples as possible)
+    // order 0: contiguous tile range per block (keeps one block inside as few samples as possible);
+    // order 1 / 2: tiles dealt round-robin so that the whole grid sweeps M upwards / downwards in time - a sweep that
+    // starts where the producer of x finished finds those rows still in L2
     const int per = (num_tiles + gridDim.x - 1) / gridDim.x;
     const int t_begin = blockIdx.x * per;
     const int t_end = min(num_tiles, t_begin + per);
-    const int my_tiles = max(0, t_end - t_begin);
+    const int my_tiles = order == 0 ? max(0, t_end - t_begin)
+                                    : (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    auto tile_of = [&](int i) {
+        if (order == 0) return t_begin + i;
+        const int g = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+        return order == 2 ? num_tiles - 1 - g : g;
+    };
     if (threadIdx.x == 0) {
         for (int s = 0; s < kLnStages; ++s) mbar_init(&full_bar[s], 1);
         fence_barrier_init();
         fence_proxy_async();
     }
     __syncthreads();
+    pdl_wait();
+    pdl_trigger();
     auto issue = [&](int i) {  // thread 0: load tile t_begin + i into stage i % kLnStages
-        const int tile = t_begin + i;
+        const int tile = tile_of(i);
         const int rows = min(kLnRows, M - tile * kLnRows);
         const uint32_t bytes = static_cast<uint32_t>(rows) * D * 4;
         uint64_t* bar = &full_bar[i % kLnStages];
@@ -176,7 +186,7 @@ ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, c
     for (int i = 0; i < my_tiles; ++i) {
         const int stage = i % kLnStages;
         const uint32_t parity = (i / kLnStages) & 1;
-        const int row = (t_begin + i) * kLnRows + warp;
+        const int row = tile_of(i) * kLnRows + warp;
         const bool ok = row < M;
         // modulation vectors first: their L2 latency overlaps the wait for the row data
         float4 sh[NV], sc[NV];

@@ -114,6 +114,26 @@ static cudaError_t launch_gemm_inst(cudaStream_t s, const CUtensorMap& ta, const
 }
 
 // 2-CTA pair kernel (256 x 256 tile per cluster of two CTAs)
+// Launch with (optionally) the programmatic-stream-serialization attribute: see pdl_wait() in common.cuh.
+static int g_pdl = -1;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args&&... args) {
+    if (g_pdl < 0) g_pdl = env_int("LFM_PDL", 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    if (g_pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int EPI>
 static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb,
                                      const CUtensorMap& tout, int M, int N, int K, const GemmEpi& ep,
@@ -130,9 +150,8 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
     int clusters = g_num_sms / 2;
     if (tiles < clusters) clusters = tiles;
     static const int split_env = env_int("LFM_GEMM_SPLIT", 1);
-    kern<<<2 * clusters, kG2Threads, kG2SmemBytes, s>>>(ta, tb, tout, tbh != nullptr ? *tbh : tb, M, N, K, ep, cg,
-                                                        (tbh != nullptr && split_env) ? 1 : 0, ksplit, split_row_pitch);
-    return cudaGetLastError();
+    return launch_k(kern, 2 * clusters, kG2Threads, kG2SmemBytes, s, ta, tb, tout, tbh != nullptr ? *tbh : tb, M, N, K, ep, cg,
+                    (tbh != nullptr && split_env) ? 1 : 0, ksplit, split_row_pitch);
 }
 
 // 4-CTA cluster kernel (two pairs sharing A by multicast; 256 x 512 block per cluster)
@@ -226,7 +245,7 @@ static cudaError_t launch_attention_inst(cudaStream_t s, const CUtensorMap& tq, 
 
 template <int NV>
 static cudaError_t launch_ln_inst(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
-                                  int mod_stride, int rows_per_sample, int M) {
+                                  int mod_stride, int rows_per_sample, int M, int order) {
     static bool attr_set = false;
     const int smem = kLnStages * kLnRows * NV * 128 * 4;
     auto kern = ln_modulate_kernel<NV>;
@@ -237,23 +256,22 @@ static cudaError_t launch_ln_inst(cudaStream_t s, const float* x, __nv_bfloat16*
     }
     const int tiles = (M + kLnRows - 1) / kLnRows;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    kern<<<grid, 256, smem, s>>>(x, y, shift, scale, mod_stride, rows_per_sample, M);
-    return cudaGetLastError();
+    return launch_k(kern, grid, 256, smem, s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
 }
 static cudaError_t launch_ln(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
-                             int mod_stride, int rows_per_sample, int M, int D) {
+                             int mod_stride, int rows_per_sample, int M, int D, int order = 0) {
     switch (D / 128) {
-        case 2: return launch_ln_inst<2>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
-        case 3: return launch_ln_inst<3>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
-        case 6: return launch_ln_inst<6>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
-        case 8: return launch_ln_inst<8>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
-        case 9: return launch_ln_inst<9>(s, x, y, shift, scale, mod_stride, rows_per_sample, M);
+        case 2: return launch_ln_inst<2>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
+        case 3: return launch_ln_inst<3>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
+        case 6: return launch_ln_inst<6>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
+        case 8: return launch_ln_inst<8>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
+        case 9: return launch_ln_inst<9>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
         default: return cudaErrorInvalidValue;
     }
 }
 
 static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, const CUtensorMap& tout, int B, int H, int D,
-                                     int variant = 2) {
+                                     int variant = 2, int reverse = 0) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attention2_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
@@ -266,7 +284,7 @@ static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, con
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
     if (variant == 3)
-        attention3_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
+        return launch_k(attention3_t256_d64, grid, kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
     else
         attention2_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
     return cudaGetLastError();
@@ -309,6 +327,9 @@ struct lfm_ctx {
     std::string err;
     int64_t launches = 0;
     int attn_variant = 0;  // 0 = P in TMEM, 1 = P via smem
+    int zigzag = 0;        // LFM_ZIGZAG: alternate the row-sweep direction of consecutive kernels (L2 reuse)
+    int l2_persist_mb = 0; // LFM_L2_PERSIST_MB: pin (part of) the fp32 residual stream in L2 (access-policy window)
+    float l2_hit_ratio = 1.0f;
     int bn_qkv = 256, bn_proj = 256, bn_fc1 = 256, bn_fc2 = 256, bn_mod = 256;
 
     std::unordered_map<std::string, ParamSlot> params;
@@ -428,6 +449,9 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     ctx->chw = ctx->C * ctx->HW * ctx->HW;
     ctx->Nmod = (6 * ctx->L + 2) * ctx->D;
     ctx->attn_variant = env_int("LFM_ATTN_VARIANT", 3);
+    ctx->zigzag = env_int("LFM_ZIGZAG", 1);
+    ctx->l2_persist_mb = env_int("LFM_L2_PERSIST_MB", 0);
+    ctx->l2_hit_ratio = env_int("LFM_L2_HIT_PCT", 100) / 100.0f;
     const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
 
     if (dev_alloc(ctx, &ctx->pos, (size_t)T * D)) return 1;
@@ -672,37 +696,84 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
     patch_embed_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, x_rows, ctx->pe_w, ctx->pe_b, ctx->pos, ctx->x_tok, D, ctx->G,
                                                    ctx->C, M);
     LAUNCH_OK();
+    if (ctx->l2_persist_mb > 0) {
+        // experiment: keep the residual stream (read by both LayerNorms, read-modify-written by proj and fc2) L2-resident
+        static bool limit_set = false;
+        if (!limit_set) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)ctx->l2_persist_mb << 20);
+            limit_set = true;
+        }
+        cudaStreamAttrValue av{};
+        size_t bytes = (size_t)M * D * sizeof(float);
+        int max_win = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
+        av.accessPolicyWindow.base_ptr = ctx->x_tok;
+        av.accessPolicyWindow.num_bytes = bytes;
+        av.accessPolicyWindow.hitRatio = ctx->l2_hit_ratio;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaError_t e = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+        if (e != cudaSuccess) {
+            static bool warned = false;
+            if (!warned) fprintf(stderr, "lfm_b200: access policy window not applied: %s\n", cudaGetErrorString(e));
+            warned = true;
+            (void)cudaGetLastError();
+        }
+    }
+    // L2 zig-zag (LFM_ZIGZAG): consecutive kernels sweep the token rows in opposite directions, so each starts on the
+    // rows its producer wrote last (still L2-resident) instead of the rows that were evicted first.
+    const int zig = ctx->zigzag;
+    int dir = 1;  // patch_embed wrote x_tok upwards
+    auto next_dir = [&]() {
+        const int d = zig ? dir : 0;
+        dir ^= 1;
+        return d;
+    };
     for (int l = 0; l < L; ++l) {
         BlockW& b = ctx->blk[l];
         const float* mb = ctx->mod + (size_t)l * 6 * D;  // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
-        CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb, mb + D, Nmod, T, M, D));
-        ctx->launches++;
+        {
+            const int d = next_dir();
+            CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb, mb + D, Nmod, T, M, D, zig ? 1 + d : 0));
+            ctx->launches++;
+        }
         {
             GemmEpi ep{b.b_qkv, ctx->qkv, 3 * D, nullptr, 0, T};
+            ep.reverse_m = next_dir();
             CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv, &b.tmh_qkv, &ctx->tm64_xn));
             ctx->launches++;
         }
-        if (ctx->attn_variant >= 2)
-            CUDA_OK(launch_attention2(s, ctx->tm_qkv_kv, ctx->tm_attn, rows, ctx->H, D, ctx->attn_variant));
-        else if (ctx->attn_variant == 0)
-            CUDA_OK(launch_attention_inst<true>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
-        else
-            CUDA_OK(launch_attention_inst<false>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
-        ctx->launches++;
+        {
+            const int d = next_dir();
+            if (ctx->attn_variant >= 2)
+                CUDA_OK(launch_attention2(s, ctx->tm_qkv_kv, ctx->tm_attn, rows, ctx->H, D, ctx->attn_variant, d));
+            else if (ctx->attn_variant == 0)
+                CUDA_OK(launch_attention_inst<true>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
+            else
+                CUDA_OK(launch_attention_inst<false>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
+            ctx->launches++;
+        }
         {
             GemmEpi ep{b.b_proj, ctx->x_tok, D, mb + 2 * D, Nmod, T};
+            ep.reverse_m = next_dir();
             CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok, &b.tmh_proj, &ctx->tm64_attn));
             ctx->launches++;
         }
-        CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D));
-        ctx->launches++;
+        {
+            const int d = next_dir();
+            CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D, zig ? 1 + d : 0));
+            ctx->launches++;
+        }
         {
             GemmEpi ep{b.b_fc1, ctx->hmid, Hd, nullptr, 0, T};
+            ep.reverse_m = next_dir();
             CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_fc1, M, Hd, D, EPI_BIAS_GELU_BF16, ctx->bn_fc1, ep, &ctx->tmo_hmid, &b.tmh_fc1, &ctx->tm64_xn));
             ctx->launches++;
         }
         {
             GemmEpi ep{b.b_fc2, ctx->x_tok, D, mb + 5 * D, Nmod, T};
+            ep.reverse_m = next_dir();
             CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep, &ctx->tmo_xtok, &b.tmh_fc2, &ctx->tm64_hmid));
             ctx->launches++;
         }
