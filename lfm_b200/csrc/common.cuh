@@ -244,6 +244,20 @@ LFM_DEVICE float warp_max(float v) {
     return v;
 }
 
+// L2 eviction-priority policies for bulk-async (TMA) traffic.  The fp32 residual stream (67 MB at batch 64) is re-read by
+// every LayerNorm and read-modify-written by every residual GEMM: marked evict_last it stays resident in the 126 MB L2
+// while the larger activations (qkv, MLP hidden) stream through with normal priority.
+LFM_DEVICE uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+LFM_DEVICE uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
 // start while its predecessor drains; it must not touch global memory the predecessor reads or writes before
 // pdl_wait() (which returns once ALL prerequisite grids have completed and flushed).  pdl_trigger() lets the NEXT

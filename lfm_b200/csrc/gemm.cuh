@@ -38,6 +38,8 @@ struct GemmEpi {
     // Pair kernel: walk the M blocks from the last to the first.  Consecutive kernels of a network alternate
     // direction so that each one starts on the rows its producer touched LAST - the part still resident in L2.
     int reverse_m = 0;
+    // Pair kernel, EPI_GATE_RESID_F32: the TMA reduce-add into the residual stream carries the evict_last L2 policy.
+    int l2_keep = 0;
 };
 constexpr double kGnFixScale = 268435456.0;  // 2^28
 
@@ -101,6 +103,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================== TMA producer =====================

@@ -109,6 +109,13 @@ LFM_DEVICE void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, in
                  : "memory");
 }
 
+LFM_DEVICE void tma_reduce_add_2d_hint(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, uint64_t policy) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+                 : "memory");
+}
+
 // Epilogue math for 32 accumulator columns of one row -> f[32] (bias, GELU, gate).
 template <int EPI>
 LFM_DEVICE void epilogue_math(const uint32_t* v, float* f, const GemmEpi& ep, int n0, int N, const float* gate_row) {
@@ -380,6 +387,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
         // for the gated residual (x += g * (acc + b) is applied at L2: the SM never reads x).
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
+        const uint64_t keep_policy = ep.l2_keep ? l2_policy_evict_last() : 0;
         uint8_t* stg0 = smem_stage + (warp - 4) * 4096;  // one staging tile per warp (measured: a second one at the
         constexpr int sbuf = 0;                           // cost of a pipeline stage does not pay)
         constexpr bool kBf16Out = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
@@ -419,7 +427,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0 && nbase + c * 32 < N) {
-                        if (EPI == EPI_GATE_RESID_F32)
+                        if (EPI == EPI_GATE_RESID_F32 && ep.l2_keep)
+                            tma_reduce_add_2d_hint(&tmap_out, stg, nbase + c * 32, row0, keep_policy);
+                        else if (EPI == EPI_GATE_RESID_F32)
                             tma_reduce_add_2d(&tmap_out, stg, nbase + c * 32, row0);
                         else
                             tma_store_2d(&tmap_out, stg, nbase + c * 32, row0);
@@ -444,7 +454,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0 && nbase + (c + 1) * 32 < N) {
-                        if (EPI == EPI_GATE_RESID_F32)
+                        if (EPI == EPI_GATE_RESID_F32 && ep.l2_keep)
+                            tma_reduce_add_2d_hint(&tmap_out, stg, nbase + (c + 1) * 32, row0, keep_policy);
+                        else if (EPI == EPI_GATE_RESID_F32)
                             tma_reduce_add_2d(&tmap_out, stg, nbase + (c + 1) * 32, row0);
                         else
                             tma_store_2d(&tmap_out, stg, nbase + (c + 1) * 32, row0);

@@ -141,11 +141,21 @@ LFM_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, u
                  : "memory");
 }
 
+LFM_DEVICE void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
 template <int NV>  // NV = D / 128 float4 per lane
 __global__ void __launch_bounds__(256, 1)
 ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ shift,
-                   const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M, int order) {
+                   const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M, int order_flags) {
     constexpr int D = NV * 128;
+    const int order = order_flags & 3;          // tile order (below)
+    const bool keep = (order_flags & 4) != 0;   // x is the residual stream: load with the evict_last L2 policy
+    const uint64_t policy = keep ? l2_policy_evict_last() : 0;
     constexpr uint32_t kStageBytes = kLnRows * D * 4;
     extern __shared__ __align__(128) uint8_t ln_smem[];
     __shared__ __align__(8) uint64_t full_bar[kLnStages];
@@ -178,7 +188,10 @@ ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, c
         const uint32_t bytes = static_cast<uint32_t>(rows) * D * 4;
         uint64_t* bar = &full_bar[i % kLnStages];
         mbar_arrive_expect_tx(bar, bytes);
-        bulk_load_1d(ln_smem + (i % kLnStages) * kStageBytes, x + static_cast<size_t>(tile) * kLnRows * D, bytes, bar);
+        if (keep)
+            bulk_load_1d_hint(ln_smem + (i % kLnStages) * kStageBytes, x + static_cast<size_t>(tile) * kLnRows * D, bytes, bar, policy);
+        else
+            bulk_load_1d(ln_smem + (i % kLnStages) * kStageBytes, x + static_cast<size_t>(tile) * kLnRows * D, bytes, bar);
     };
     if (threadIdx.x == 0)
         for (int i = 0; i < kLnStages && i < my_tiles; ++i) issue(i);
@@ -547,6 +560,8 @@ __global__ void transpose_f32_kernel(const float* __restrict__ in, float* __rest
 
 // fp32 -> bf16 weight repack (nn.Linear weights are already [N, K] K-major: a plain cast)
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         const float4 v = *reinterpret_cast<const float4*>(in + i);

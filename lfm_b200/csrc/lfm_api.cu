@@ -97,30 +97,13 @@ static int env_int(const char* name, int dflt) {
 
 static int g_num_sms = 0;
 
-template <int BN, int EPI>
-static cudaError_t launch_gemm_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-                                    const GemmEpi& ep) {
-    static bool attr_set = false;
-    auto kern = gemm_bf16_tcgen05<BN, EPI>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    const int tiles = ((M + kGemmBlockM - 1) / kGemmBlockM) * ((N + BN - 1) / BN);
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
-    return cudaGetLastError();
-}
-
-// 2-CTA pair kernel (256 x 256 tile per cluster of two CTAs)
-// Launch with (optionally) the programmatic-stream-serialization attribute: see pdl_wait() in common.cuh.
+// Launch with (by default; LFM_PDL=0 disables) the programmatic-stream-serialization attribute: see pdl_wait() in common.cuh.
 static int g_pdl = -1;
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_k(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args&&... args) {
-    if (g_pdl < 0) g_pdl = env_int("LFM_PDL", 0);
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t s, Args&&... args) {
+    if (g_pdl < 0) g_pdl = env_int("LFM_PDL", 1);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
@@ -133,7 +116,24 @@ static cudaError_t launch_k(void (*kern)(KArgs...), unsigned grid, unsigned bloc
     }
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+// ONLY for kernels that execute pdl_wait() before their first global-memory access.
 
+template <int BN, int EPI>
+static cudaError_t launch_gemm_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                                    const GemmEpi& ep) {
+    static bool attr_set = false;
+    auto kern = gemm_bf16_tcgen05<BN, EPI>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tiles = ((M + kGemmBlockM - 1) / kGemmBlockM) * ((N + BN - 1) / BN);
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    return launch_k(kern, dim3(grid), kGemmThreads, GemmCfg<BN>::kSmemBytes, s, ta, tb, M, N, K, ep);
+}
+
+// 2-CTA pair kernel (256 x 256 tile per cluster of two CTAs)
 template <int EPI>
 static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb,
                                      const CUtensorMap& tout, int M, int N, int K, const GemmEpi& ep,
@@ -150,7 +150,7 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
     int clusters = g_num_sms / 2;
     if (tiles < clusters) clusters = tiles;
     static const int split_env = env_int("LFM_GEMM_SPLIT", 1);
-    return launch_k(kern, 2 * clusters, kG2Threads, kG2SmemBytes, s, ta, tb, tout, tbh != nullptr ? *tbh : tb, M, N, K, ep, cg,
+    return launch_k(kern, dim3(2 * clusters), kG2Threads, kG2SmemBytes, s, ta, tb, tout, tbh != nullptr ? *tbh : tb, M, N, K, ep, cg,
                     (tbh != nullptr && split_env) ? 1 : 0, ksplit, split_row_pitch);
 }
 
@@ -256,7 +256,7 @@ static cudaError_t launch_ln_inst(cudaStream_t s, const float* x, __nv_bfloat16*
     }
     const int tiles = (M + kLnRows - 1) / kLnRows;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    return launch_k(kern, grid, 256, smem, s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
+    return launch_k(kern, dim3(grid), 256, smem, s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
 }
 static cudaError_t launch_ln(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
                              int mod_stride, int rows_per_sample, int M, int D, int order = 0) {
@@ -284,7 +284,7 @@ static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, con
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
     if (variant == 3)
-        return launch_k(attention3_t256_d64, grid, kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
+        return launch_k(attention3_t256_d64, dim3(grid), kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
     else
         attention2_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
     return cudaGetLastError();
@@ -328,8 +328,7 @@ struct lfm_ctx {
     int64_t launches = 0;
     int attn_variant = 0;  // 0 = P in TMEM, 1 = P via smem
     int zigzag = 0;        // LFM_ZIGZAG: alternate the row-sweep direction of consecutive kernels (L2 reuse)
-    int l2_persist_mb = 0; // LFM_L2_PERSIST_MB: pin (part of) the fp32 residual stream in L2 (access-policy window)
-    float l2_hit_ratio = 1.0f;
+    int l2_hint = 0;       // LFM_L2_HINT: evict_last L2 policy on the residual stream's TMA traffic (measured: no gain)
     int bn_qkv = 256, bn_proj = 256, bn_fc1 = 256, bn_fc2 = 256, bn_mod = 256;
 
     std::unordered_map<std::string, ParamSlot> params;
@@ -450,8 +449,7 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     ctx->Nmod = (6 * ctx->L + 2) * ctx->D;
     ctx->attn_variant = env_int("LFM_ATTN_VARIANT", 3);
     ctx->zigzag = env_int("LFM_ZIGZAG", 1);
-    ctx->l2_persist_mb = env_int("LFM_L2_PERSIST_MB", 0);
-    ctx->l2_hit_ratio = env_int("LFM_L2_HIT_PCT", 100) / 100.0f;
+    ctx->l2_hint = env_int("LFM_L2_HINT", 0);
     const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
 
     if (dev_alloc(ctx, &ctx->pos, (size_t)T * D)) return 1;
@@ -665,6 +663,11 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
         CUDA_OK(cudaGetLastError());                  \
         ctx->launches++;                              \
     } while (0)
+#define LAUNCH_K(...)                                 \
+    do {                                              \
+        CUDA_OK(launch_k(__VA_ARGS__));               \
+        ctx->launches++;                              \
+    } while (0)
 
 #include "unet_host.inc"
 
@@ -696,31 +699,6 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
     patch_embed_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, x_rows, ctx->pe_w, ctx->pe_b, ctx->pos, ctx->x_tok, D, ctx->G,
                                                    ctx->C, M);
     LAUNCH_OK();
-    if (ctx->l2_persist_mb > 0) {
-        // experiment: keep the residual stream (read by both LayerNorms, read-modify-written by proj and fc2) L2-resident
-        static bool limit_set = false;
-        if (!limit_set) {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)ctx->l2_persist_mb << 20);
-            limit_set = true;
-        }
-        cudaStreamAttrValue av{};
-        size_t bytes = (size_t)M * D * sizeof(float);
-        int max_win = 0;
-        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-        if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
-        av.accessPolicyWindow.base_ptr = ctx->x_tok;
-        av.accessPolicyWindow.num_bytes = bytes;
-        av.accessPolicyWindow.hitRatio = ctx->l2_hit_ratio;
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaError_t e = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
-        if (e != cudaSuccess) {
-            static bool warned = false;
-            if (!warned) fprintf(stderr, "lfm_b200: access policy window not applied: %s\n", cudaGetErrorString(e));
-            warned = true;
-            (void)cudaGetLastError();
-        }
-    }
     // L2 zig-zag (LFM_ZIGZAG): consecutive kernels sweep the token rows in opposite directions, so each starts on the
     // rows its producer wrote last (still L2-resident) instead of the rows that were evicted first.
     const int zig = ctx->zigzag;
@@ -735,7 +713,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         const float* mb = ctx->mod + (size_t)l * 6 * D;  // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
         {
             const int d = next_dir();
-            CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb, mb + D, Nmod, T, M, D, zig ? 1 + d : 0));
+            CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb, mb + D, Nmod, T, M, D, (zig ? 1 + d : 0) | (ctx->l2_hint ? 4 : 0)));
             ctx->launches++;
         }
         {
@@ -757,12 +735,13 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         {
             GemmEpi ep{b.b_proj, ctx->x_tok, D, mb + 2 * D, Nmod, T};
             ep.reverse_m = next_dir();
+            ep.l2_keep = ctx->l2_hint;
             CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok, &b.tmh_proj, &ctx->tm64_attn));
             ctx->launches++;
         }
         {
             const int d = next_dir();
-            CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D, zig ? 1 + d : 0));
+            CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D, (zig ? 1 + d : 0) | (ctx->l2_hint ? 4 : 0)));
             ctx->launches++;
         }
         {
@@ -774,6 +753,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         {
             GemmEpi ep{b.b_fc2, ctx->x_tok, D, mb + 5 * D, Nmod, T};
             ep.reverse_m = next_dir();
+            ep.l2_keep = ctx->l2_hint;
             CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep, &ctx->tmo_xtok, &b.tmh_fc2, &ctx->tm64_hmid));
             ctx->launches++;
         }

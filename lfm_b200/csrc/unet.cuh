@@ -28,6 +28,8 @@ constexpr int kGnMaxJ = 16;  // C <= 2048
 template <int J>  // J = C / 128 float4 slots per lane per pixel
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(Src2 s, int HW, int nchunk, double* __restrict__ partial) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     extern __shared__ float s_part[];  // [8 warps][J][32 lanes][2]
     constexpr int C = J * 128, cpg = C / 32;
     constexpr int U = J >= 8 ? 1 : (J >= 4 ? 2 : 4);  // pixels in flight per warp: ~8 independent 512 B requests
@@ -98,6 +100,8 @@ struct GnApplyArgs {
 template <int J>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(GnApplyArgs a) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     extern __shared__ float s_coef[];  // [2][C]: y = x * A[c] + Bc[c]   (GroupNorm affine and FiLM folded per channel)
     __shared__ float s_mean[32], s_rstd[32];
     constexpr int C = J * 128, cpg = C / 32;
@@ -174,6 +178,8 @@ gn_apply_kernel(GnApplyArgs a) {
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, int x_rows, const float* __restrict__ Wt /*[C,4,3,3]*/,
                const float* __restrict__ bias, float* __restrict__ out, int H, int W, int C) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     extern __shared__ float s_in[];  // [4][3][W + 2]
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int bs = b % x_rows;
@@ -249,6 +255,8 @@ conv_out_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ W
 
 // out.2 on the tensor cores: the pair GEMM writes [B*H*W, 4] (NHWC); this scatters it to the NCHW velocity.
 __global__ void nhwc4_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int HW) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // pixel index
     if (i >= static_cast<size_t>(B) * HW) return;
     const float4 v = *reinterpret_cast<const float4*>(in + i * 4);
@@ -262,6 +270,8 @@ __global__ void nhwc4_to_nchw_kernel(const float* __restrict__ in, float* __rest
 
 // Upsample: nearest x2 of the fp32 stream -> bf16 operand of the following conv3x3 (unet.py:92-99).
 __global__ void upsample2x_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     const size_t n4 = static_cast<size_t>(B) * 2 * H * 2 * W * (C / 4);
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -281,6 +291,8 @@ __global__ void upsample2x_cast_kernel(const float* __restrict__ x, __nv_bfloat1
 // One warp per query; lanes split the keys for the scores and the channels for the output.  fp32 softmax.
 __global__ void __launch_bounds__(256)
 attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int C, int heads) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     __shared__ float s_q[8][256];
     __shared__ float s_p[8][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -338,6 +350,8 @@ attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 // Split-K epilogue: out[m, n] (+)= bias[n] + sum_s partial[s][m][n], slabs added in a fixed order (deterministic).
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, size_t slab /*elements*/, const float* __restrict__ bias,
                                      float* __restrict__ out, int N, size_t n4, int accumulate) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + (i % (N / 4)));
@@ -359,6 +373,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, s
 // Used when (2 T ch + pad) bf16 fit in shared memory (all LFM presets: T <= 64, ch <= 256).
 __global__ void __launch_bounds__(256)
 attention_small_smem_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int C, int heads) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     extern __shared__ __align__(16) uint8_t s_kv[];
     __shared__ float s_q[8][256];
     __shared__ float s_p[8][256];
@@ -434,6 +450,8 @@ attention_small_smem_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
 template <bool UP>
 __global__ void resample2x_kernel(const __nv_bfloat16* __restrict__ a_in, __nv_bfloat16* __restrict__ a_out,
                                   const float* __restrict__ x_in, float* __restrict__ x_out, int B, int H, int W, int C) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     const int Ho = UP ? 2 * H : H / 2, Wo = UP ? 2 * W : W / 2;
     const size_t n4 = static_cast<size_t>(B) * Ho * Wo * (C / 4);
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -497,6 +515,8 @@ __global__ void edm_qkv_bias_repack_kernel(const float* __restrict__ b, float* _
 // Labels of one network batch for the one-hot column gather of map_label (EDM.py:822-829): row b reads table row
 // y[b]; under forward_with_cfg (drop_half_label) rows >= rows/2 read the all-zero row `null_row`.
 __global__ void edm_labels_kernel(const long long* __restrict__ y, long long* __restrict__ out, int rows, int drop_from, int null_row) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= rows) return;
     long long v = y[b];
@@ -525,6 +545,8 @@ __global__ void conv_out_weight_repack_kernel(const float* __restrict__ w, float
 
 // sinusoidal timestep features of arbitrary even width (nn.py:103-121; cos first, raw t)
 __global__ void timestep_features_dim_kernel(const float* __restrict__ t, int t_numel, float* __restrict__ tf, int B, int dim) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     const int b = blockIdx.x;
     const int half = dim / 2;
     for (int i = threadIdx.x; i < dim; i += blockDim.x) {
@@ -542,6 +564,8 @@ __global__ void __launch_bounds__(256)
 skinny_linear_gen_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ in, int B,
                          int N, int K, const float* __restrict__ table, const long long* __restrict__ idx, int mode,
                          float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * 8 + warp;
     if (j >= N) return;
