@@ -442,6 +442,138 @@ attention_small_smem_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
 }
 
 // ------------------------------------------------------------------------------------------------
+// Attention core for the short token grids (T = 16 or 64 tokens per sample) on the tensor cores: warp-level
+// mma.sync m16n8k16 (bf16 in, fp32 accumulate) - these tiles are far too small for a tcgen05 pipeline, and the SIMT
+// kernels above are instruction-issue bound (about 1000 warp instructions per query).  Same layouts as
+// attention_small_kernel: qkv [B*T, 3C] with channel = head*3ch + {q,k,v}*ch + c, out [B*T, C].
+// One warp owns 16 query rows: S = Q K^T stays in registers, softmax on the accumulator fragments (fp32), the bf16
+// probabilities are re-used directly as the A fragments of P V (no shared-memory round trip).
+// T = 64: one (sample, head) per 4-warp block; T = 16: four (sample, head) pairs per block, one warp each.
+LFM_DEVICE void ldmatrix_x4(uint32_t* r, const void* smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem_ptr)));
+}
+LFM_DEVICE void ldmatrix_x4_trans(uint32_t* r, const void* smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem_ptr)));
+}
+LFM_DEVICE void mma_bf16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int T, int CH>
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int C, int heads, int n_items) {
+    pdl_wait();
+    pdl_trigger();
+    constexpr int ITEMS = T == 16 ? 4 : 1;  // (sample, head) pairs per block
+    static_assert(T == 16 || T == 64, "one or four 16-row warps per (sample, head)");
+    constexpr int LD = CH + 8;              // row pitch in elements: +16 bytes keeps ldmatrix bank-conflict free
+    constexpr int CPR = CH / 8;             // 16-byte chunks per row
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(att_smem);  // [ITEMS][q,k,v][T][LD]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t ld = static_cast<size_t>(3) * C;
+    for (int i = threadIdx.x; i < ITEMS * 3 * T * CPR; i += 128) {
+        const int c8 = i % CPR;
+        int r = i / CPR;
+        const int t = r % T;
+        r /= T;
+        const int which = r % 3, it = r / 3;
+        const int item = blockIdx.x * ITEMS + it;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (item < n_items) {
+            const int b = item / heads, h = item % heads;
+            v = *reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(b) * T + t) * ld + static_cast<size_t>(h) * 3 * CH + which * CH + c8 * 8);
+        }
+        *reinterpret_cast<uint4*>(sm + (static_cast<size_t>(it * 3 + which) * T + t) * LD + c8 * 8) = v;
+    }
+    __syncthreads();
+    const int it = ITEMS == 1 ? 0 : warp;
+    const int item = blockIdx.x * ITEMS + it;
+    if (item >= n_items) return;
+    const int r0 = ITEMS == 1 ? warp * 16 : 0;
+    const __nv_bfloat16* sQ = sm + static_cast<size_t>(it * 3 + 0) * T * LD;
+    const __nv_bfloat16* sK = sm + static_cast<size_t>(it * 3 + 1) * T * LD;
+    const __nv_bfloat16* sV = sm + static_cast<size_t>(it * 3 + 2) * T * LD;
+
+    float acc_s[T / 8][4];
+#pragma unroll
+    for (int j = 0; j < T / 8; ++j) acc_s[j][0] = acc_s[j][1] = acc_s[j][2] = acc_s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < CH / 16; ++kk) {
+        uint32_t a[4];
+        ldmatrix_x4(a, sQ + (r0 + (lane & 15)) * LD + kk * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int j2 = 0; j2 < T / 16; ++j2) {
+            uint32_t bk[4];
+            ldmatrix_x4(bk, sK + (j2 * 16 + (lane & 7) + ((lane >> 4) << 3)) * LD + kk * 16 + ((lane >> 3) & 1) * 8);
+            mma_bf16_16816(acc_s[2 * j2], a, bk[0], bk[1]);
+            mma_bf16_16816(acc_s[2 * j2 + 1], a, bk[2], bk[3]);
+        }
+    }
+    // softmax over the keys of rows g = lane / 4 (values [0], [1]) and g + 8 ([2], [3]); a row lives in one quad
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < T / 8; ++j) {
+        m0 = fmaxf(m0, fmaxf(acc_s[j][0], acc_s[j][1]));
+        m1 = fmaxf(m1, fmaxf(acc_s[j][2], acc_s[j][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    const float sl2 = rsqrtf(static_cast<float>(CH)) * 1.4426950408889634f;  // (ch^-1/4)^2 = 1/sqrt(ch), in log2 units
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < T / 8; ++j) {
+        acc_s[j][0] = exp2f((acc_s[j][0] - m0) * sl2);
+        acc_s[j][1] = exp2f((acc_s[j][1] - m0) * sl2);
+        acc_s[j][2] = exp2f((acc_s[j][2] - m1) * sl2);
+        acc_s[j][3] = exp2f((acc_s[j][3] - m1) * sl2);
+        l0 += acc_s[j][0] + acc_s[j][1];
+        l1 += acc_s[j][2] + acc_s[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+    float acc_o[CH / 8][4];
+#pragma unroll
+    for (int n = 0; n < CH / 8; ++n) acc_o[n][0] = acc_o[n][1] = acc_o[n][2] = acc_o[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < T / 16; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(acc_s[2 * kk][0], acc_s[2 * kk][1]);
+        pa[1] = pack_bf16x2(acc_s[2 * kk][2], acc_s[2 * kk][3]);
+        pa[2] = pack_bf16x2(acc_s[2 * kk + 1][0], acc_s[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(acc_s[2 * kk + 1][2], acc_s[2 * kk + 1][3]);
+#pragma unroll
+        for (int n2 = 0; n2 < CH / 16; ++n2) {
+            uint32_t bv[4];
+            ldmatrix_x4_trans(bv, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + n2 * 16 + (lane >> 4) * 8);
+            mma_bf16_16816(acc_o[2 * n2], pa, bv[0], bv[1]);
+            mma_bf16_16816(acc_o[2 * n2 + 1], pa, bv[2], bv[3]);
+        }
+    }
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    const int b = item / heads, h = item % heads;
+    const int row = r0 + (lane >> 2);
+    __nv_bfloat16* o0 = out + (static_cast<size_t>(b) * T + row) * C + static_cast<size_t>(h) * CH + (lane & 3) * 2;
+    __nv_bfloat16* o1 = o0 + static_cast<size_t>(8) * C;
+#pragma unroll
+    for (int n = 0; n < CH / 8; ++n) {
+        *reinterpret_cast<uint32_t*>(o0 + n * 8) = pack_bf16x2(acc_o[n][0] * inv0, acc_o[n][1] * inv0);
+        *reinterpret_cast<uint32_t*>(o1 + n * 8) = pack_bf16x2(acc_o[n][2] * inv1, acc_o[n][3] * inv1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // EDM-style ADM (DhariwalUNet, reference models/EDM.py) additions.
 //
 // Resampling inside a UNetBlock (EDM.py:101-134 with resample_filter [1, 1]): `down` = 2x2 mean, `up` = nearest x2.

@@ -33,7 +33,8 @@ def launches(src, dst):
         v = v / 1000 if u == "ns" else (v * 1000 if u == "ms" else v)
         seq.append((re.sub(r"\(.*", "", row[ix["Kernel Name"]]).replace("void ", ""), v))
     starts = [i for i, (n, _) in enumerate(seq) if "timestep_features" in n]
-    a, b = starts[0], starts[1]
+    # the last COMPLETE evaluation in the capture (earlier ones include first-touch effects)
+    a, b = (starts[-2], starts[-1]) if len(starts) > 1 else (starts[0], len(seq))
     agg = collections.OrderedDict()
     tot = 0.0
     for n, v in seq[a:b]:
@@ -42,13 +43,14 @@ def launches(src, dst):
         agg[n][1] += 1
         tot += v
     out = io.StringIO()
-    out.write("# ncu launch list, one network evaluation (NFE) of `python bench.py --steps 1 --warmup 3`\n\n")
+    title = sys.argv[4] if len(sys.argv) > 4 else "DiT-L/2, batch 64 (M = 16384 token rows), `python bench.py --steps 1 --warmup 3`"
+    out.write(f"# ncu launch list, one network evaluation (NFE): {title}\n\n")
     out.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare SHARES).\n")
-    out.write(f"DiT-L/2, batch 64 (M = 16384 token rows); {b - a} kernel launches per NFE; sum {tot / 1000:.3f} ms.\n\n")
+    out.write(f"{b - a} kernel launches per NFE; sum {tot / 1000:.3f} ms.\n\n")
     out.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
     for n, (v, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         out.write(f"| `{n}` | {c} | {v:.1f} | {100 * v / tot:.1f}% |\n")
-    out.write("\nFirst transformer block in launch order (us):\n\n")
+    out.write("\nFirst kernels in launch order (us):\n\n")
     for n, v in seq[a:a + 13]:
         out.write(f"- {v:8.1f}  {n}\n")
     open(dst, "w").write(out.getvalue())
