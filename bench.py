@@ -299,6 +299,15 @@ def main():
         value = imgs / (ms_total * 1e-3)
         e2e_value = imgs / (ms_e2e * 1e-3)
         tflops = value * NFE * flops_nfe / 1e12 / world  # per GPU
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = usable_threads()
+            v, dt, sample = cpu_baseline(threads)
+            cpu = {"value": round(v, 5), "unit": "images/s", "cores": threads, "kind": "port", "sample": sample}
+        elif world == 1:
+            time.sleep(3.0)
+        # the dominant kernel is timed ALONE against the burst peak: the CPU leg above (or the pause) lets the board
+        # leave the power-capped state of the long run first, as in the measurement of the burst peak itself
         roof = time_dominant_kernel(device, peaks) if world == 1 else None
         line = {
             "metric": "images/sec DiT-L/2 32x32 latents Euler-50", "value": round(value, 3), "unit": "images/s",
@@ -320,10 +329,8 @@ def main():
         }
         if roof is not None:
             line["roofline"] = roof
-        if world == 1 and not args.no_cpu_baseline:
-            threads = usable_threads()
-            v, dt, sample = cpu_baseline(threads)
-            line["cpu_baseline"] = {"value": round(v, 5), "unit": "images/s", "cores": threads, "kind": "port", "sample": sample}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

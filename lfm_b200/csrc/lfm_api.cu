@@ -556,7 +556,6 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
         CUDA_OK(cudaDeviceSynchronize());
     }
     s.set = true;
-    ctx->finalized = ctx->finalized && true;
     return 0;
 }
 
@@ -814,9 +813,7 @@ extern "C" int lfm_forward(lfm_ctx* ctx, const float* t, int t_numel, const floa
         return fail(ctx, "lfm_forward: UNetModel has no forward_with_cfg; cfg_scale must be <= 1");
     if (cfg_scale > 1.0f) {
         if (B % 2 != 0) return fail(ctx, "lfm_forward: forward_with_cfg needs an even batch (got %d)", B);
-        if (t_numel != 1) {
-            // the reference passes t[2n]; both halves carry the same times (x halves are identical)
-        }
+        // a vector t has 2n entries in the reference; both halves carry the same times (the x halves are identical)
         const int n_img = B / 2;
         if (launch_network(ctx, s, t, t_numel, x, n_img, yl, B)) return 1;
         const size_t n = (size_t)n_img * ctx->chw;

@@ -449,6 +449,10 @@ attention_small_smem_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16
 // One warp owns 16 query rows: S = Q K^T stays in registers, softmax on the accumulator fragments (fp32), the bf16
 // probabilities are re-used directly as the A fragments of P V (no shared-memory round trip).
 // T = 64: one (sample, head) per 4-warp block; T = 16: four (sample, head) pairs per block, one warp each.
+LFM_DEVICE void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+LFM_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 LFM_DEVICE void ldmatrix_x4(uint32_t* r, const void* smem_ptr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -485,13 +489,15 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
         r /= T;
         const int which = r % 3, it = r / 3;
         const int item = blockIdx.x * ITEMS + it;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (item < n_items) {
+        __nv_bfloat16* dst = sm + (static_cast<size_t>(it * 3 + which) * T + t) * LD + c8 * 8;
+        if (item < n_items) {  // asynchronous copies: all of a thread's 16-byte requests are in flight together
             const int b = item / heads, h = item % heads;
-            v = *reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(b) * T + t) * ld + static_cast<size_t>(h) * 3 * CH + which * CH + c8 * 8);
+            cp_async_16(dst, qkv + (static_cast<size_t>(b) * T + t) * ld + static_cast<size_t>(h) * 3 * CH + which * CH + c8 * 8);
+        } else {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
         }
-        *reinterpret_cast<uint4*>(sm + (static_cast<size_t>(it * 3 + which) * T + t) * LD + c8 * 8) = v;
     }
+    cp_async_wait_all();
     __syncthreads();
     const int it = ITEMS == 1 ? 0 : warp;
     const int item = blockIdx.x * ITEMS + it;

@@ -1,5 +1,5 @@
 """Throughput of the other BASELINE.json configs on ONE GPU (the headline line is bench.py; these are records for
-DESIGN.md / profiles, not bench lines).  python scripts/bench_configs.py [cfg3 cfg4 cfg5]"""
+DESIGN.md / profiles, not bench lines).  python scripts/bench_configs.py [cfg3 cfg4 cfg5 edm]"""
 import json
 import os
 import sys
@@ -11,7 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import lfm_b200  # noqa: E402
-from lfm_b200.synthetic import synthetic_state_dict, synthetic_unet_state_dict  # noqa: E402
+from lfm_b200.synthetic import synthetic_edm_state_dict, synthetic_state_dict, synthetic_unet_state_dict  # noqa: E402
 
 dev = torch.device("cuda:0")
 
@@ -84,11 +84,32 @@ def cfg5():
     return out
 
 
+def edm():
+    # imnet_adm preset (test_args/imnet_adm.txt): DhariwalUNet, 1000 classes, CFG 1.25, dopri5 atol=rtol=1e-5; 32 images
+    # => 64-row forward per NFE
+    with torch.device("meta"):
+        net = lfm_b200.DhariwalUNet(img_resolution=32, in_channels=4, out_channels=4, label_dim=1000, model_channels=256,
+                                    channel_mult=(1, 2, 3, 4), num_blocks=2, attn_resolutions=(16, 8, 4), max_batch=64)
+    sd = synthetic_edm_state_dict(net, 1)
+    net = net.to_empty(device="cpu")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(32, 4, 32, 32, generator=g).to(dev)
+    y = torch.randint(0, 1000, (32,), generator=g).to(dev)
+    mk = dict(y=torch.cat([y, torch.zeros_like(y)]), cfg_scale=1.25)
+    args = types.SimpleNamespace(method="dopri5", atol=1e-5, rtol=1e-5, cfg_scale=1.25, compute_nfe=True)
+    ms = timeit(lambda: lfm_b200.sample_from_model(net, torch.cat([x, x]), mk, args), reps=1)
+    s = net.last_stats
+    return {"config": "imnet_adm DhariwalUNet CFG1.25 dopri5 1e-5, 32 img (64-row forward)", "ms": ms, **s,
+            "images_per_s": 32 / ms * 1e3, "nfe_img_per_s": s["nfe"] * 32 / ms * 1e3, "tflops": s["nfe"] * 64 * 73.05e9 / ms / 1e9}
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5"]
+    which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5", "edm"]
     res = []
     for w in which:
-        r = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}[w]()
+        r = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "edm": edm}[w]()
         res.extend(r if isinstance(r, list) else [r])
         torch.cuda.empty_cache()
     for r in res:
