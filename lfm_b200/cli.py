@@ -92,12 +92,14 @@ def build_parser():
 
 
 def load_model(args, device):
-    from . import create_network
-    from .synthetic import synthetic_state_dict
+    from . import DhariwalUNet, UNetModel, create_network
+    from .synthetic import synthetic_edm_state_dict, synthetic_state_dict, synthetic_unet_state_dict
     with torch.device("meta"):
         model = create_network(args)
     if args.synthetic_init is not None:
-        sd = synthetic_state_dict(model, args.synthetic_init)
+        make = (synthetic_unet_state_dict if isinstance(model, UNetModel)
+                else synthetic_edm_state_dict if isinstance(model, DhariwalUNet) else synthetic_state_dict)
+        sd = make(model, args.synthetic_init)
     else:
         path = "./saved_info/latent_flow/{}/{}/model_{}.pth".format(args.dataset, args.exp, args.epoch_id)
         ckpt = torch.load(path, map_location="cpu")

@@ -37,3 +37,26 @@ def test_determ_is_batch_size_independent():
     a = get_generator("determ", 32, 7).randn(8, 4, 4, 4)
     b = get_generator("determ", 32, 7).randn(3, 4, 4, 4)
     assert torch.equal(a[:3], b)
+
+
+def test_cli_builds_every_native_network_family():
+    """The reference command lines of the three network families (bash_scripts/run_test.sh with test_args/*.txt) parse
+    and build through create_network with seeded weights - on the CPU, without running the network."""
+    import torch
+    from lfm_b200 import DhariwalUNet, DiT, UNetModel
+    from lfm_b200.cli import build_parser, load_model
+    common = ["--image_size", "256", "--f", "8", "--num_in_channels", "4", "--num_out_channels", "4", "--nf", "128",
+              "--synthetic_init", "3", "--no_decode"]
+    cases = [
+        (["--model_type", "DiT-S/2", "--num_classes", "1", "--label_dropout", "0."], DiT),
+        (["--model_type", "adm", "--use_origin_adm", "--ch_mult", "1", "2", "--attn_resolutions", "2", "--num_res_blocks", "1",
+          "--num_heads", "2"], UNetModel),
+        (["--model_type", "adm", "--ch_mult", "1", "2", "--attn_resolutions", "16", "--num_res_blocks", "1", "--label_dim", "7"],
+         DhariwalUNet),
+    ]
+    for extra, cls in cases:
+        args = build_parser().parse_args(common + extra)
+        net = load_model(args, torch.device("cpu"))
+        assert isinstance(net, cls)
+        assert all(torch.isfinite(p).all() for p in net.state_dict().values())
+        assert float(sum(p.abs().sum() for p in net.parameters())) > 0
