@@ -114,7 +114,9 @@ int lfm_finalize(lfm_ctx* ctx, int max_batch);
  *   (NULL = the table's last row, models/DiT.py:259-260).
  *   cfg_scale <= 1: v_out = DiT(t, x, y).
  *   cfg_scale  > 1: forward_with_cfg - B must be even, rows [B/2, B) of y hold the null class; the first half
- *   of x is evaluated with both label halves and v_out = cat[g, g], g = u + s (c - u). */
+ *   of x is evaluated with both label halves and v_out = cat[g, g], g = u + s (c - u).
+ *   Labels are validated by the caller (the Python mirror raises like nn.Embedding / one_hot would); on the device an
+ *   out-of-range label is clamped to the table, never read out of bounds. */
 int lfm_forward(lfm_ctx* ctx, const float* t, int t_numel, const float* x, const int64_t* y, int B, float cfg_scale,
                 float* v_out, void* stream);
 

@@ -57,7 +57,8 @@ skinny_linear_kernel(const float* __restrict__ W, const float* __restrict__ bias
         if (lane == 0) {
             float v = acc + bj;
             if (MODE == 1) {
-                const long long row = (idx != nullptr) ? idx[b] : static_cast<long long>(null_row);
+                long long row = (idx != nullptr) ? idx[b] : static_cast<long long>(null_row);
+                row = row < 0 ? 0 : (row > null_row ? null_row : row);  // never read outside the table (null_row = last row)
                 v += table[static_cast<size_t>(row) * N + j];
             }
             v = silu(v);

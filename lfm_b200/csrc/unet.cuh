@@ -210,6 +210,54 @@ conv_in_kernel(const float* __restrict__ x, int x_rows, const float* __restrict_
     }
 }
 
+// Same convolution, register-blocked: a thread owns channel c and walks the output row in strips of 8 pixels; per
+// (input channel, filter row) it fetches the 10 input values of the strip with three vector loads (warp-wide
+// broadcasts from shared memory) and issues 24 FMAs - 27 instructions per 8 outputs and tap row instead of 48.
+// Requires W % 8 == 0 (rows padded to W + 4 floats so that every strip starts 16-byte aligned).
+__global__ void __launch_bounds__(256)
+conv_in_strip_kernel(const float* __restrict__ x, int x_rows, const float* __restrict__ Wt /*[C,4,3,3]*/,
+                     const float* __restrict__ bias, float* __restrict__ out, int H, int W, int C) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ __align__(16) float s_in2[];  // [4][3][W + 4]: position p holds column p - 1
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int bs = b % x_rows;
+    const int WP = W + 4;
+    for (int i = threadIdx.x; i < 4 * 3 * WP; i += blockDim.x) {
+        const int c = i / (3 * WP), r = (i / WP) % 3, w = i % WP - 1;
+        const int hh = h + r - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && w >= 0 && w < W) v = x[((static_cast<size_t>(bs) * 4 + c) * H + hh) * W + w];
+        s_in2[i] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float wreg[36];
+#pragma unroll
+        for (int i = 0; i < 36; ++i) wreg[i] = __ldg(Wt + static_cast<size_t>(c) * 36 + i);
+        const float bc = bias[c];
+        float* orow = out + (static_cast<size_t>(b) * H + h) * W * C + c;
+        for (int w0 = 0; w0 < W; w0 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) acc[p] = bc;
+#pragma unroll
+            for (int cr = 0; cr < 12; ++cr) {  // (input channel, filter row)
+                const float* ip = s_in2 + cr * WP + w0;
+                const float4 a0 = *reinterpret_cast<const float4*>(ip);
+                const float4 a1 = *reinterpret_cast<const float4*>(ip + 4);
+                const float2 a2 = *reinterpret_cast<const float2*>(ip + 8);
+                const float in[10] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
+                const float k0 = wreg[cr * 3], k1 = wreg[cr * 3 + 1], k2 = wreg[cr * 3 + 2];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) acc[p] = fmaf(k2, in[p + 2], fmaf(k1, in[p + 1], fmaf(k0, in[p], acc[p])));
+            }
+#pragma unroll
+            for (int p = 0; p < 8; ++p) orow[static_cast<size_t>(w0 + p) * C] = acc[p];
+        }
+    }
+}
+
 // out.2: conv3x3(C -> 4), pad 1, on the GN+SiLU'd bf16 NHWC operand -> NCHW fp32 velocity (unet.py:591-595).
 // One warp per output pixel, lane = 8-channel slice; weights [4][9][C] fp32 in shared memory.
 __global__ void __launch_bounds__(256)
@@ -701,7 +749,7 @@ __global__ void timestep_features_dim_kernel(const float* __restrict__ t, int t_
 __global__ void __launch_bounds__(256)
 skinny_linear_gen_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ in, int B,
                          int N, int K, const float* __restrict__ table, const long long* __restrict__ idx, int mode,
-                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int max_row) {
     pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -722,7 +770,11 @@ skinny_linear_gen_kernel(const float* __restrict__ W, const float* __restrict__ 
         acc = warp_sum(acc);
         if (lane == 0) {
             float v = acc + bj;
-            if (mode == 1 && table != nullptr && idx != nullptr) v += table[static_cast<size_t>(idx[b]) * N + j];
+            if (mode == 1 && table != nullptr && idx != nullptr) {
+                long long row = idx[b];
+                row = row < 0 ? 0 : (row > max_row ? max_row : row);  // never read outside the table
+                v += table[static_cast<size_t>(row) * N + j];
+            }
             v = silu(v);
             if (mode == 0)
                 out_f32[static_cast<size_t>(b) * N + j] = v;
