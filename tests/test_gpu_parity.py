@@ -502,6 +502,19 @@ def test_edm_imnet_preset_full_size_properties(dev):
     assert rel_l2(vc[:8].cpu(), (vu + 1.25 * (v - vu)).cpu()) < 1e-4
 
 
+def test_edm_unsupported_configuration_fails_loudly(dev):
+    """Self-attention on a 32x32 grid (1024 tokens) has no native kernel: lfm_create_edm must refuse (and release the
+    half-built context), never fall back; a supported network created afterwards works."""
+    net = lfm_b200.DhariwalUNet(img_resolution=32, in_channels=4, out_channels=4, model_channels=128, channel_mult=(1, 2),
+                                num_blocks=1, attn_resolutions=(32,)).to(dev)
+    with pytest.raises(RuntimeError, match="not supported"):
+        net(torch.tensor(0.5, device=dev), torch.randn(1, 4, 32, 32, device=dev))
+    ok = lfm_b200.DhariwalUNet(img_resolution=16, in_channels=4, out_channels=4, model_channels=128, channel_mult=(1, 2),
+                               num_blocks=1, attn_resolutions=(8,)).to(dev)
+    v = ok(torch.tensor(0.5, device=dev), torch.randn(2, 4, 16, 16, device=dev))
+    assert v.shape == (2, 4, 16, 16) and float(v.abs().max()) == 0.0     # reference init: zero output convolution
+
+
 # ------------------------------------------------------------------------------------------------ edges / CLI
 
 
