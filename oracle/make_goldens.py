@@ -185,6 +185,13 @@ def make_edm_goldens(g):
             out["y_cfg"] = y2
             out["t_cfg"] = torch.tensor([0.4] * (2 * B))
             out["v_cfg_1p25"] = net.forward_with_cfg(out["t_cfg"], x2, y2, cfg_scale=1.25)
+            # the reference's own fixed-step samplers on this network, with its CFG denoiser dispatch
+            # (karras_sample.py:42-49 -> DhariwalUNet.forward_with_cfg) and without labels' second half mattering
+            ks = sys.modules["sampler.karras_sample"]
+            common = dict(device="cpu", clip_denoised=False, sigma_min=1e-5, sigma_max=1.0, s_tmin=0.0, s_tmax=1.0, s_churn=0.0)
+            out["cfg_euler4"] = ks.karras_sample(net, x2, steps=4, sampler="euler", model_kwargs=dict(y=y2, cfg_scale=1.25), **common)
+            out["cfg_heun3"] = ks.karras_sample(net, x2, steps=3, sampler="heun", model_kwargs=dict(y=y2, cfg_scale=1.25), **common)
+            out["y_euler3"] = ks.karras_sample(net, x, steps=3, sampler="euler", model_kwargs=dict(y=y), **common)
         else:
             out["v"] = net(tv, x)
         np.savez_compressed(os.path.join(OUT, name + ".npz"),

@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from oracle import edm as oedm
+from oracle import solvers as osol
 from tests._util import T, load_golden, rel_l2
 
 
@@ -54,3 +55,18 @@ def test_edm_plan_preset():
     assert max(m["cin"] for m in dec) == 2048
     fl = oedm.edm_flops_per_sample(cfg)
     assert 50e9 < fl < 200e9
+
+
+def test_edm_samplers_match_reference():
+    """oracle.solvers driven by oracle.edm vs the reference's own karras_sample on its own DhariwalUNet, including the
+    CFG denoiser dispatch (karras_sample.py:42-49 -> forward_with_cfg, EDM.py:847-861)."""
+    g = load_golden("edm_mini_cond")
+    cfg = edm_cfg_from_golden(g)
+    sd = oedm.synthetic_state_dict(cfg, int(g["weight_seed"]))
+    x, y, y2 = T(g["x"]), T(g["y"]), T(g["y_cfg"])
+    x2 = torch.cat([x, x], 0)
+    fc = lambda tt, xx: oedm.edm_forward_with_cfg(sd, cfg, tt, xx, y2, 1.25)  # noqa: E731
+    assert rel_l2(osol.karras_sample(fc, x2, 4, "euler"), g["cfg_euler4"]) < 2e-5
+    assert rel_l2(osol.karras_sample(fc, x2, 3, "heun"), g["cfg_heun3"]) < 2e-5
+    f = lambda tt, xx: oedm.edm_forward(sd, cfg, tt, xx, y)  # noqa: E731
+    assert rel_l2(osol.karras_sample(f, x, 3, "euler"), g["y_euler3"]) < 2e-5
