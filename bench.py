@@ -184,6 +184,14 @@ def cpu_baseline(threads, seconds_hint=20):
     return B * nfe / dt / NFE, dt, f"DiT-L/2 fp32 oracle, batch {B}, {nfe} Euler NFE in {dt:.2f}s, scaled to Euler-{NFE} images/s"
 
 
+def workload_config(world):
+    """The `config` object of both arms (the driver compares them)."""
+    return {"workload": f"{MODEL} 32x32x4 latents, Euler-{NFE} (step_size {STEP_SIZE}), batch {BATCH}/GPU, "
+                        f"synthetic non-degenerate init (seed {WEIGHT_SEED}), {'dp' + str(world)}",
+            "l2": "inputs larger than L2: 0.9 GB of weights + 0.7 GB of activations stream per NFE (L2 = 126 MB)",
+            "global_batch": BATCH * world, "nfe_per_image": NFE}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm (oracle port; the reference is pure Python and cannot travel to
     the GPU box) on the host CPU with all the threads it can use; rank 0 only."""
@@ -209,7 +217,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "images/sec DiT-L/2 32x32 latents Euler-50", "value": value, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{MODEL} 32x32x4 latents, Euler-{NFE} (step_size {STEP_SIZE}), batch {BATCH}/GPU, synthetic init"},
+            "config": workload_config(int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -313,10 +321,7 @@ def main():
             "metric": "images/sec DiT-L/2 32x32 latents Euler-50", "value": round(value, 3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{MODEL} 32x32x4 latents, Euler-{NFE} (step_size {STEP_SIZE}), batch {BATCH}/GPU, "
-                                   f"synthetic non-degenerate init (seed {WEIGHT_SEED}), {'dp' + str(world)}",
-                       "l2": "inputs larger than L2: 0.9 GB of weights + 0.7 GB of activations stream per NFE (L2 = 126 MB)",
-                       "global_batch": BATCH * world, "nfe_per_image": NFE},
+            "config": workload_config(world),
             "nfe_img_per_s": round(value * NFE, 1),
             "e2e": {"value": round(e2e_value, 3), "unit": "images/s", "h2d_bytes_per_step": BATCH * chw * 4,
                     "d2h_bytes_per_step": BATCH * chw * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
