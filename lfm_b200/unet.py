@@ -60,8 +60,7 @@ class UNetModel(_NativeNet):
             raise NotImplementedError("native UNetModel implements the LFM preset configuration only: "
                                       "use_scale_shift_norm=True, resblock_updown=False, conv_resample=True, "
                                       "legacy attention order, dims=2, fp32 parameters")
-        if dropout:
-            raise NotImplementedError("dropout is a training-time option")
+        self.dropout = dropout   # a training-time option: the sampling path runs in eval mode, where Dropout is the identity
         self.image_size, self.in_channels, self.model_channels, self.out_channels = image_size, in_channels, model_channels, out_channels
         self.num_res_blocks = num_res_blocks
         self.attention_resolutions = tuple(int(a) for a in attention_resolutions)
