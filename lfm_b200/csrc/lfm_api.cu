@@ -15,6 +15,7 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "attention3.cuh"
+#include "attention4.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -278,11 +279,15 @@ static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, con
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(attention3_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(attention4_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
+        if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
+    if (variant == 4)  // experimental (attention4.cuh); not the default
+        return launch_k(attention4_t256_d64, dim3(grid), kA4Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
     if (variant == 3)
         return launch_k(attention3_t256_d64, dim3(grid), kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
     else
