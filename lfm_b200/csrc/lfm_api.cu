@@ -279,15 +279,20 @@ static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, con
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(attention3_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(attention4_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
-        if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
-    if (variant == 4)  // experimental (attention4.cuh); not the default
+    if (variant == 4) {  // experimental (attention4.cuh); not the default - nothing of it runs unless asked for
+        static bool attr4_set = false;
+        if (!attr4_set) {
+            cudaError_t e = cudaFuncSetAttribute(attention4_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
+            if (e != cudaSuccess) return e;
+            attr4_set = true;
+        }
         return launch_k(attention4_t256_d64, dim3(grid), kA4Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
+    }
     if (variant == 3)
         return launch_k(attention3_t256_d64, dim3(grid), kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
     else
