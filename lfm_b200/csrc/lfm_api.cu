@@ -3,6 +3,7 @@
 #include "../../include/lfm_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -15,7 +16,7 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "attention3.cuh"
-#include "attention4.cuh"
+#include "attention5.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -96,7 +97,32 @@ static int env_int(const char* name, int dflt) {
 // ------------------------------------------------------------------------------------------------
 // kernel launch helpers
 
-static int g_num_sms = 0;
+// SM count of the device the calling thread is working on: set at every API entry from the ctx (a ctx is bound to
+// one device; several contexts on different devices may live in one process).
+static thread_local int g_num_sms = 0;
+
+// Opt-in for more than 48 KB of dynamic shared memory.  cudaFuncSetAttribute applies to the CURRENT device only, so
+// the "done" flag is kept per device (one bit each); safe to call from several host threads.
+struct DevOnce {
+    std::atomic<uint64_t> mask{0};
+};
+template <typename K>
+static cudaError_t smem_opt_in(DevOnce& once, K kern, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (once.mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) once.mask.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+static int query_num_sms() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+}
 
 // Launch with (by default; LFM_PDL=0 disables) the programmatic-stream-serialization attribute: see pdl_wait() in common.cuh.
 static int g_pdl = -1;
@@ -122,13 +148,9 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, unsigned block, s
 template <int BN, int EPI>
 static cudaError_t launch_gemm_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                                     const GemmEpi& ep) {
-    static bool attr_set = false;
+    static DevOnce once;
     auto kern = gemm_bf16_tcgen05<BN, EPI>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = smem_opt_in(once, kern, GemmCfg<BN>::kSmemBytes)) return e;
     const int tiles = ((M + kGemmBlockM - 1) / kGemmBlockM) * ((N + BN - 1) / BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     return launch_k(kern, dim3(grid), kGemmThreads, GemmCfg<BN>::kSmemBytes, s, ta, tb, M, N, K, ep);
@@ -140,13 +162,9 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
                                      const CUtensorMap& tout, int M, int N, int K, const GemmEpi& ep,
                                      ConvGeom cg = ConvGeom{0, 0, 0, 0, 1}, const CUtensorMap* tbh = nullptr, int ksplit = 1,
                                      int split_row_pitch = 0) {
-    static bool attr_set = false;
+    static DevOnce once;
     auto kern = gemm2_bf16_tcgen05<EPI>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2SmemBytes);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = smem_opt_in(once, kern, kG2SmemBytes)) return e;
     const int tiles = ((M + 255) / 256) * ((N + kG2BlockN - 1) / kG2BlockN) * ksplit;
     int clusters = g_num_sms / 2;
     if (tiles < clusters) clusters = tiles;
@@ -159,10 +177,14 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
 template <int EPI>
 static cudaError_t launch_gemm4_inst(cudaStream_t s, const CUtensorMap& ta64, const CUtensorMap& tb, const CUtensorMap& tout,
                                      int M, int N, int K, const GemmEpi& ep) {
-    static int max_clusters = -1;
+    static int max_clusters_dev[64];  // per device; 0 = not queried yet
+    static DevOnce once;
     auto kern = gemm4_bf16_tcgen05<EPI>;
-    if (max_clusters < 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG4SmemBytes);
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    int& max_clusters = max_clusters_dev[dev & 63];
+    if (max_clusters <= 0) {
+        cudaError_t e = smem_opt_in(once, kern, kG4SmemBytes);
         if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(4 * (g_num_sms / 4));
@@ -231,14 +253,9 @@ static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUte
 template <bool P_TMEM>
 static cudaError_t launch_attention_inst(cudaStream_t s, const CUtensorMap& tq, const CUtensorMap& tkv,
                                          __nv_bfloat16* out, int B, int H, int D, float* dbg_s) {
-    static bool attr_set = false;
+    static DevOnce once;
     auto kern = attention_t256_d64<P_TMEM>;
-    if (!attr_set) {
-        cudaError_t e =
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<P_TMEM>());
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = smem_opt_in(once, kern, attn_smem_bytes<P_TMEM>())) return e;
     const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e), head_dim = 64
     kern<<<dim3(2, H, B), kAttnThreads, attn_smem_bytes<P_TMEM>(), s>>>(tq, tkv, out, D, scale_log2e, dbg_s);
     return cudaGetLastError();
@@ -247,14 +264,10 @@ static cudaError_t launch_attention_inst(cudaStream_t s, const CUtensorMap& tq, 
 template <int NV>
 static cudaError_t launch_ln_inst(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
                                   int mod_stride, int rows_per_sample, int M, int order) {
-    static bool attr_set = false;
+    static DevOnce once;
     const int smem = kLnStages * kLnRows * NV * 128 * 4;
     auto kern = ln_modulate_kernel<NV>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (cudaError_t e = smem_opt_in(once, kern, smem)) return e;
     const int tiles = (M + kLnRows - 1) / kLnRows;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
     return launch_k(kern, dim3(grid), 256, smem, s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
@@ -273,25 +286,17 @@ static cudaError_t launch_ln(cudaStream_t s, const float* x, __nv_bfloat16* y, c
 
 static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, const CUtensorMap& tout, int B, int H, int D,
                                      int variant = 2, int reverse = 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention2_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(attention3_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static DevOnce once2, once3;
+    if (cudaError_t e = smem_opt_in(once2, attention2_t256_d64, kA2SmemBytes)) return e;
+    if (cudaError_t e = smem_opt_in(once3, attention3_t256_d64, kA2SmemBytes)) return e;
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
-    if (variant == 4) {  // experimental (attention4.cuh); not the default - nothing of it runs unless asked for
-        static bool attr4_set = false;
-        if (!attr4_set) {
-            cudaError_t e = cudaFuncSetAttribute(attention4_t256_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2SmemBytes);
-            if (e != cudaSuccess) return e;
-            attr4_set = true;
-        }
-        return launch_k(attention4_t256_d64, dim3(grid), kA4Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
+    if (variant == 5) {  // per-tile MMA issuers, staggered ("ping-pong") - attention5.cuh
+        static DevOnce once5;
+        static const int stagger = env_int("LFM_ATTN_STAGGER", 1);
+        if (cudaError_t e = smem_opt_in(once5, attention5_t256_d64, kA2SmemBytes)) return e;
+        return launch_k(attention5_t256_d64, dim3(grid), kA5Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse, stagger);
     }
     if (variant == 3)
         return launch_k(attention3_t256_d64, dim3(grid), kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
@@ -331,6 +336,7 @@ struct lfm_ctx {
     int arch = LFM_ARCH_DIT;
     UNetState* un = nullptr;
     int device = 0;
+    int num_sms = 0;
     int D = 0, L = 0, H = 0, T = 0, G = 0, C = 0, Hd = 0, Nmod = 0, HW = 0, chw = 0;
     int max_rows = 0;
     bool finalized = false;
@@ -446,7 +452,7 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     ctx->d = *desc;
     ctx->device = device;
     CUDA_OK(cudaSetDevice(device));
-    g_num_sms = prop.multiProcessorCount;
+    g_num_sms = ctx->num_sms = prop.multiProcessorCount;
     ctx->D = desc->hidden_size;
     ctx->L = desc->depth;
     ctx->H = desc->num_heads;
@@ -527,6 +533,7 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
         if (shape[i] != s.shape[i])
             return fail(ctx, "lfm_set_param(%s): dim %d is %lld, expected %lld", key, i, (long long)shape[i], (long long)s.shape[i]);
     CUDA_OK(cudaSetDevice(ctx->device));
+    g_num_sms = ctx->num_sms;
     if (!s.to_bf16) {
         CUDA_OK(cudaMemcpy(s.dst, ptr, s.numel * sizeof(float), cudaMemcpyDefault));
     } else {
@@ -606,6 +613,7 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
     if (ctx->finalized && max_batch <= ctx->max_rows) return 0;
     if (ctx->finalized) return fail(ctx, "lfm_finalize: already finalized for %d rows; create a new ctx for %d", ctx->max_rows, max_batch);
     CUDA_OK(cudaSetDevice(ctx->device));
+    g_num_sms = ctx->num_sms;
     if (ctx->arch == LFM_ARCH_UNET) {
         if (unet_finalize(ctx, max_batch)) return 1;
         if (alloc_solver_state(ctx, max_batch)) return 1;
@@ -769,13 +777,9 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
     }
     {
         const float* mf = ctx->mod + (size_t)6 * L * D;  // shift | scale
-        static bool attr_set = false;
+        static DevOnce once;
         const int smem = 16 * D * (int)sizeof(float);
-        if (!attr_set) {
-            // opt in once for the largest supported width (hidden_size <= 1536)
-            CUDA_OK(cudaFuncSetAttribute(final_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1536 * 4));
-            attr_set = true;
-        }
+        CUDA_OK(smem_opt_in(once, final_layer_kernel, 16 * 1536 * 4));  // largest supported width (hidden_size <= 1536)
         int grid = (M + 7) / 8;
         if (grid > 2 * g_num_sms) grid = 2 * g_num_sms;
         final_layer_kernel<<<grid, 256, smem, s>>>(ctx->x_tok, mf, mf + D, Nmod, ctx->fin_w, ctx->fin_b, ctx->v_net, M, D,
@@ -817,6 +821,7 @@ extern "C" int lfm_forward(lfm_ctx* ctx, const float* t, int t_numel, const floa
     if (t == nullptr || x == nullptr || v_out == nullptr) return fail(ctx, "lfm_forward: null tensor");
     if (t_numel != 1 && t_numel != B) return fail(ctx, "lfm_forward: t has %d elements, expected 1 or %d", t_numel, B);
     CUDA_OK(cudaSetDevice(ctx->device));
+    g_num_sms = ctx->num_sms;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long* yl = reinterpret_cast<const long long*>(y);
     if (cfg_scale > 1.0f && ctx->arch == LFM_ARCH_UNET && ctx_unet_variant(ctx) == 0)
@@ -927,6 +932,7 @@ extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const 
     if (x_inout == nullptr || t_grid_host == nullptr) return fail(ctx, "lfm_sample_fixed: null tensor");
     if (cfg_scale > 1.0f && y == nullptr) return fail(ctx, "lfm_sample_fixed: CFG needs labels");
     CUDA_OK(cudaSetDevice(ctx->device));
+    g_num_sms = ctx->num_sms;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)B_img * ctx->chw;
     const bool has_y = y != nullptr;
@@ -1107,6 +1113,7 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
     if (!(t0 > t1)) return fail(ctx, "lfm_sample_dopri5: expects t0 > t1 (reference integrates t: 1 -> 0)");
     if (cfg_scale > 1.0f && y == nullptr) return fail(ctx, "lfm_sample_dopri5: CFG needs labels");
     CUDA_OK(cudaSetDevice(ctx->device));
+    g_num_sms = ctx->num_sms;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     if (join_in(ctx, user)) return 1;
     Dopri d{ctx, ctx->stream, B_img, nullptr, cfg_scale, (size_t)B_img * ctx->chw};
@@ -1264,13 +1271,8 @@ extern "C" int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float*
     if (K % 64 != 0 || N % 8 != 0) return fail(ctx, "lfm_dbg_gemm: K must be a multiple of 64 and N of 8");
     if (block_n != 128 && block_n != 256 && block_n != kGemmPair && block_n != kGemmQuad)
         return fail(ctx, "lfm_dbg_gemm: block_n must be 128, 256, 512 (CTA pair) or 1024 (4-CTA cluster)");
-    if (g_num_sms == 0) {
-        int dev = 0;
-        CUDA_OK(cudaGetDevice(&dev));
-        cudaDeviceProp prop;
-        CUDA_OK(cudaGetDeviceProperties(&prop, dev));
-        g_num_sms = prop.multiProcessorCount;
-    }
+    g_num_sms = query_num_sms();
+    if (g_num_sms <= 0) return fail(ctx, "no CUDA device");
     CUtensorMap ta, tb;
     if (!make_tmap_bf16(&ta, a_bf16, M, K, 128) || !make_tmap_bf16(&tb, w_bf16, N, K, weight_box_rows(block_n)))
         return fail(ctx, "lfm_dbg_gemm: tensor map encode failed");
@@ -1295,13 +1297,8 @@ extern "C" int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, in
         return fail(ctx, "lfm_dbg_attention: tensor map encode failed");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (variant >= 2) {
-        if (g_num_sms == 0) {
-            int dev = 0;
-            CUDA_OK(cudaGetDevice(&dev));
-            cudaDeviceProp prop;
-            CUDA_OK(cudaGetDeviceProperties(&prop, dev));
-            g_num_sms = prop.multiProcessorCount;
-        }
+        g_num_sms = query_num_sms();
+        if (g_num_sms <= 0) return fail(ctx, "no CUDA device");
         CUtensorMap tout;
         if (!make_tmap_bf16(&tout, out_bf16, M, D, 128)) return fail(ctx, "lfm_dbg_attention: tensor map encode failed");
         CUDA_OK(launch_attention2(s, tkv, tout, B, H, D, variant));

@@ -144,6 +144,13 @@ class DhariwalUNet(_NativeNet):
         _lib.check(lib.lfm_create_edm(C.byref(d), dev_index, C.byref(ctx)))
         return ctx
 
+    def uses_labels(self):
+        return bool(self.label_dim)          # without map_label a y argument is ignored (EDM.py:823)
+
+    def check_label_range(self, y):
+        if y.numel() and (int(y.min()) < 0 or int(y.max()) >= self.label_dim):
+            raise RuntimeError("Class values must be smaller than num_classes.")   # what F.one_hot raises
+
     def _labels(self, y, B, drop_half_label):
         """one_hot(y, label_dim) semantics (EDM.py:824): labels must be class ids; a dropped label is encoded as
         index label_dim (the all-zero row of the native table)."""
@@ -152,8 +159,7 @@ class DhariwalUNet(_NativeNet):
         y = torch.as_tensor(y).to(torch.int64)
         if y.numel() != B:
             raise ValueError(f"y has {y.numel()} labels, expected {B}")
-        if int(y.min()) < 0 or int(y.max()) >= self.label_dim:
-            raise RuntimeError("Class values must be smaller than num_classes.")   # what F.one_hot raises
+        self.check_label_range(y)
         if drop_half_label:
             y = y.clone()
             y[B // 2:] = self.label_dim

@@ -110,10 +110,20 @@ class _NativeNet(nn.Module):
             y = torch.as_tensor(y, device=x.device).to(torch.int64).contiguous()
             if y.numel() != B:
                 raise ValueError(f"y has {y.numel()} labels, expected {B}")
-            # same failure the reference's nn.Embedding would raise on an out-of-range label
-            if int(y.min()) < 0 or int(y.max()) >= self.table_rows:
-                raise IndexError("label out of range for the embedding table")
+            self._check_table_index(y)
         return t, x, y, B
+
+    def uses_labels(self):
+        return True
+
+    def _check_table_index(self, y):
+        """The failure the reference's ``nn.Embedding`` raises on an out-of-range index (the device kernels clamp)."""
+        if y.numel() and (int(y.min()) < 0 or int(y.max()) >= self.table_rows):
+            raise IndexError(f"label out of range for the embedding table ({self.table_rows} rows)")
+
+    def check_label_range(self, y):
+        """Validation of user-facing labels (solver entry points)."""
+        self._check_table_index(y)
 
     def _forward_native(self, t, x, y, cfg_scale=1.0):
         B = x.shape[0]

@@ -54,6 +54,19 @@ def _split_cfg(x, model_kwargs):
     return x.contiguous(), y, 1.0, False
 
 
+def _check_labels(net, y, rows, device):
+    """Label validation shared by every sampler entry (the same checks ``forward`` applies in ``_prep``): one label
+    per network row, each a valid row of the network's label table - the reference's ``nn.Embedding`` /
+    ``F.one_hot`` raise on an out-of-range label, and the C ABI reads exactly ``rows`` labels from the pointer."""
+    if y is None or not net.uses_labels():
+        return None
+    y = torch.as_tensor(y, device=device).to(torch.int64).reshape(-1).contiguous()
+    if y.numel() != rows:
+        raise ValueError(f"expected {rows} labels, got {y.numel()}")
+    net.check_label_range(y)
+    return y
+
+
 def _run_fixed(model, x, y, cfg_scale, t_nodes, method, t_as_vector, corrector_limit):
     net = _unwrap(model)
     if not x.is_cuda:
@@ -61,11 +74,8 @@ def _run_fixed(model, x, y, cfg_scale, t_nodes, method, t_as_vector, corrector_l
     x = x.to(torch.float32).contiguous().clone()
     n_img = x.shape[0]
     rows = 2 * n_img if cfg_scale > 1.0 else n_img
+    y = _check_labels(net, y, rows, x.device)
     ctx = net.native(rows, x.device)
-    if y is not None:
-        y = torch.as_tensor(y, device=x.device).to(torch.int64).contiguous()
-        if y.numel() != rows:
-            raise ValueError(f"expected {rows} labels, got {y.numel()}")
     grid = t_nodes.detach().to("cpu", torch.float32).contiguous()
     stats = _lib.OdeStats()
     _lib.check(_lib.load().lfm_sample_fixed(
@@ -114,9 +124,8 @@ def sample_from_model(model, x_0, model_kwargs, args):
         xf = x.to(torch.float32).contiguous().clone()
         n_img = xf.shape[0]
         rows = 2 * n_img if cfg_scale > 1.0 else n_img
+        y = _check_labels(net, y, rows, xf.device)
         ctx = net.native(rows, xf.device)
-        if y is not None:
-            y = torch.as_tensor(y, device=xf.device).to(torch.int64).contiguous()
         st = _lib.OdeStats()
         _lib.check(_lib.load().lfm_sample_dopri5(ctx, xf.data_ptr(), 1.0, 0.0, float(args.rtol), float(args.atol),
                                                  y.data_ptr() if y is not None else None, n_img, float(cfg_scale),

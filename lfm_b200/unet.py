@@ -60,6 +60,9 @@ class UNetModel(_NativeNet):
             raise NotImplementedError("native UNetModel implements the LFM preset configuration only: "
                                       "use_scale_shift_norm=True, resblock_updown=False, conv_resample=True, "
                                       "legacy attention order, dims=2, fp32 parameters")
+        if num_heads_upsample not in (-1, num_heads):
+            raise NotImplementedError("num_heads_upsample != num_heads (a different head count in the output-block "
+                                      "attention, unet.py:452-453) is not implemented natively")
         self.dropout = dropout   # a training-time option: the sampling path runs in eval mode, where Dropout is the identity
         self.image_size, self.in_channels, self.model_channels, self.out_channels = image_size, in_channels, model_channels, out_channels
         self.num_res_blocks = num_res_blocks

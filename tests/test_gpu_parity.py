@@ -95,7 +95,7 @@ def test_gemm_epilogues(dev, M, N, K, epi, bn):
     assert rel_l2(out.float().cpu(), ref.cpu()) < tol
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 5])
 @pytest.mark.parametrize("B,H", [(1, 1), (2, 4), (3, 12), (64, 16)])
 def test_attention(dev, variant, B, H):
     lib = _lib.load()
@@ -464,6 +464,16 @@ def test_edm_solvers_vs_oracle(dev):
                                  sampler="heun", model_kwargs=dict(y=y2.to(dev), cfg_scale=1.25))
     assert rel_l2(out.cpu(), osol.karras_sample(fc, torch.cat([x, x]), 4, "heun")) < TOL_UNET_NFE
     assert net.last_stats["nfe"] == 6 and torch.equal(out[:2], out[2:])
+    # the same entry point against the reference's OWN karras_sample on its own DhariwalUNet (fixtures recorded by
+    # oracle/make_goldens.py: Euler / Heun through the reference's CFG denoiser dispatch, and labels without CFG)
+    xg, yg2 = T(g["x"]), T(g["y_cfg"])
+    common = dict(clip_denoised=False, sigma_min=1e-5, sigma_max=1.0)
+    out = lfm_b200.karras_sample(net, torch.cat([xg, xg]).to(dev), 4, sampler="euler", model_kwargs=dict(y=yg2.to(dev), cfg_scale=1.25), **common)
+    assert rel_l2(out.cpu(), g["cfg_euler4"]) < TOL_UNET_NFE
+    out = lfm_b200.karras_sample(net, torch.cat([xg, xg]).to(dev), 3, sampler="heun", model_kwargs=dict(y=yg2.to(dev), cfg_scale=1.25), **common)
+    assert rel_l2(out.cpu(), g["cfg_heun3"]) < TOL_UNET_NFE
+    out = lfm_b200.karras_sample(net, xg.to(dev), 3, sampler="euler", model_kwargs=dict(y=T(g["y"]).to(dev)), **common)
+    assert rel_l2(out.cpu(), g["y_euler3"]) < TOL_UNET_NFE
     f = lambda tt, xx: oedm.edm_forward(sd, cfg, tt, xx, y)  # noqa: E731
     args = types.SimpleNamespace(method="euler", step_size=0.25, perturb=False, cfg_scale=1.0, compute_nfe=False)
     traj = lfm_b200.sample_from_model(net, x.to(dev), dict(y=y.to(dev)), args)

@@ -181,3 +181,29 @@ def test_edm_state_dict_surface_and_factory():
         small(torch.tensor(0.5), torch.randn(2, 4, 16, 16))
     with pytest.raises(RuntimeError):                              # one_hot semantics: class ids only
         small(torch.tensor(0.5), torch.randn(2, 4, 16, 16), torch.tensor([0, 5]))
+
+
+def test_sampler_label_validation():
+    """The solver entry points validate labels before handing raw pointers to the C ABI (the device kernels clamp):
+    one label per network row, each a valid table row - as nn.Embedding / F.one_hot raise in the reference."""
+    from lfm_b200 import solvers
+    net = _mini(label_dropout=0.0)                       # 10 classes, no null row: y_null = num_classes is out of range
+    assert net.table_rows == 10
+    ok = solvers._check_labels(net, torch.tensor([0, 9, 3, 3]), 4, "cpu")
+    assert ok.dtype == torch.int64 and ok.tolist() == [0, 9, 3, 3]
+    with pytest.raises(IndexError):                      # CFG against a table without a null class
+        solvers._check_labels(net, torch.tensor([1, 2, 10, 10]), 4, "cpu")
+    with pytest.raises(ValueError):                      # a short label vector (dopri5 would read past its end)
+        solvers._check_labels(net, torch.tensor([1, 2]), 4, "cpu")
+    assert solvers._check_labels(net, None, 4, "cpu") is None
+    edm = lfm_b200.DhariwalUNet(img_resolution=16, in_channels=4, out_channels=4, label_dim=5, model_channels=128,
+                                channel_mult=(1, 2), num_blocks=1, attn_resolutions=(8,))
+    with pytest.raises(RuntimeError):                    # one_hot semantics
+        solvers._check_labels(edm, torch.tensor([0, 5]), 2, "cpu")
+    edm0 = lfm_b200.DhariwalUNet(img_resolution=16, in_channels=4, out_channels=4, label_dim=0, model_channels=128,
+                                 channel_mult=(1, 2), num_blocks=1, attn_resolutions=(8,))
+    assert solvers._check_labels(edm0, torch.tensor([7]), 2, "cpu") is None   # no map_label: y is ignored (EDM.py:823)
+    with pytest.raises(NotImplementedError):
+        lfm_b200.UNetModel(image_size=32, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=1,
+                           attention_resolutions=(2,), channel_mult=(1, 2), num_heads=2, num_heads_upsample=4,
+                           use_scale_shift_norm=True)

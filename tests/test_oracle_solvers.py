@@ -5,6 +5,8 @@ restatement on closed forms, NFE counts and scipy's independent Dormand-Prince i
 """
 import math
 
+import pytest
+
 import numpy as np
 import torch
 
@@ -124,3 +126,36 @@ def test_fixed_rk_orders_on_linear_field():
     xf, _ = osol.tdq_fixed_rk(lambda t, x: a * x, x0, 1.0, "rk4")
     z = -a
     assert torch.allclose(xf, x0 * (1 + z + z * z / 2 + z ** 3 / 6 + z ** 4 / 24), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["rot", "dit"])
+def test_tdq_fixtures_from_real_torchdiffeq(name):
+    """S2 / S3 pin: the restated torchdiffeq euler / midpoint / rk4 / dopri5 against fixtures recorded from the REAL
+    package by oracle/make_tdq_goldens.py.  torchdiffeq is not in the build image, so the fixtures do not exist yet
+    and the test skips - parity for these two rows stays 'unpinned'  until they do."""
+    import os
+    import sys
+    import numpy as np
+    from tests._util import GOLDEN, rel_l2
+    path = os.path.join(GOLDEN, f"tdq_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/tdq_*.npz not recorded: torchdiffeq is absent from the image (oracle/make_tdq_goldens.py)")
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "oracle"))
+    from oracle.make_tdq_goldens import fields
+    z = np.load(path)
+    f, x0, _ = fields()[name]
+    assert np.array_equal(x0.numpy(), z["x0"])
+    for h in (0.25, 0.1, 0.02, 1.0 / 3.0):
+        key = f"euler_h{h:.6f}"
+        out, nfe = osol.tdq_euler(f, x0, h)
+        assert nfe == int(z[key + "_nfe"])
+        assert np.array_equal(osol.tdq_euler_grid(h)[:-1].numpy(), z[key + "_times"])      # the times the model sees
+        assert rel_l2(out, z[key]) < 1e-6
+    for m, hh in (("midpoint", 0.2), ("rk4", 0.2)):
+        out, nfe = osol.tdq_fixed_rk(f, x0, hh, m)
+        assert nfe == int(z[f"{m}_h{hh}_nfe"]) and rel_l2(out, z[f"{m}_h{hh}"]) < 1e-6
+    for tol in (1e-2, 1e-3, 1e-5):
+        key = f"dopri5_tol{tol:g}"
+        out, st = osol.tdq_dopri5(f, x0, rtol=tol, atol=tol)
+        assert st.nfe == int(z[key + "_nfe"])                                                # same accept/reject sequence
+        assert rel_l2(out, z[key]) < 1e-5
