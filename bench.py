@@ -9,6 +9,12 @@ step_size 0.02 => 50 NFE), batch 64 per GPU, synthetic non-degenerate weights (l
 seed 1 - the reference's own init is all-zero at the output) and Gaussian latents.  One "step" = one full
 sampling pass over one batch of 64 latents per GPU.  Metric: images/s (whole job, weak scaling).
 
+After the headline region the same process also measures, and reports under extra keys of the SAME line:
+`other_configs` (BASELINE.json configs 3, 4, 5 at this GPU count: DiT-B/2 CFG Heun-25, ADM UNet dopri5 1e-5 at N=1,
+DiT-L/2 batch-128 Euler sweep in weak and strong scaling), `gemm_vs_cublas` (the four DiT-L GEMM shapes, our kernel
+vs torch.matmul on the same box), `gpu_eager_baseline` (the reference network in eager PyTorch on this GPU: bf16
+autocast + SDPA + TF32) and `decode` (images/s including the native VAE decode).  `--no-extras` skips them.
+
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
@@ -93,17 +99,30 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm)}
 
 
-def build_model(device):
+def build_model(device, model=MODEL, num_classes=1, label_dropout=0.0, max_batch=BATCH):
     import lfm_b200
     from lfm_b200.synthetic import synthetic_state_dict
     with torch.device("meta"):
-        net = lfm_b200.DiT_models[MODEL](img_resolution=32, in_channels=4, label_dropout=0.0, num_classes=1)
+        net = lfm_b200.DiT_models[model](img_resolution=32, in_channels=4, label_dropout=label_dropout, num_classes=num_classes)
     sd = synthetic_state_dict(net, WEIGHT_SEED)
     net = net.to_empty(device="cpu")
     net.load_state_dict(sd, strict=True)
     net = net.to(device)
-    net.max_batch_hint = BATCH
+    net.max_batch_hint = max_batch
     return net
+
+
+def build_unet_celeb512(device, max_batch):
+    import lfm_b200
+    from lfm_b200.synthetic import synthetic_unet_state_dict
+    with torch.device("meta"):
+        net = lfm_b200.UNetModel(image_size=64, in_channels=4, model_channels=256, out_channels=4, num_res_blocks=2,
+                                 attention_resolutions=(16, 8), channel_mult=(1, 2, 2, 2, 4), num_heads=4,
+                                 use_scale_shift_norm=True, max_batch=max_batch)
+    sd = synthetic_unet_state_dict(net, WEIGHT_SEED)
+    net = net.to_empty(device="cpu")
+    net.load_state_dict(sd, strict=True)
+    return net.to(device)
 
 
 def time_dominant_kernel(device, peaks, iters=20):
@@ -185,16 +204,26 @@ def cpu_baseline(threads, seconds_hint=20):
 
 
 def workload_config(world):
-    """The `config` object of both arms (the driver compares them)."""
+    """The `config` object of the GPU arm."""
     return {"workload": f"{MODEL} 32x32x4 latents, Euler-{NFE} (step_size {STEP_SIZE}), batch {BATCH}/GPU, "
                         f"synthetic non-degenerate init (seed {WEIGHT_SEED}), {'dp' + str(world)}",
             "l2": "inputs larger than L2: 0.9 GB of weights + 0.7 GB of activations stream per NFE (L2 = 126 MB)",
             "global_batch": BATCH * world, "nfe_per_image": NFE}
 
 
+# The reference arm's "step" is a bounded sample of one pass: REF_NFE_PER_STEP of its 50 Euler NFE on REF_BATCH of its 64
+# latents (the driver runs --steps 20 --warmup 5; a full-batch NFE takes 5-15 s on the box's host cores).  The CPU's
+# NFE x images / s does not grow with the batch (measured: batch 16 is no faster per image than batch 4).
+REF_NFE_PER_STEP = 1
+REF_BATCH = 16
+
+
 def run_reference(args):
-    """--impl reference: the reference algorithm (oracle port; the reference is pure Python and cannot travel to
-    the GPU box) on the host CPU with all the threads it can use; rank 0 only."""
+    """--impl reference: the reference algorithm (oracle port; the reference is pure Python + absent dependencies and
+    cannot travel to the GPU box) on the host CPU with all the threads it can use; rank 0 only.  Same workload as the
+    GPU arm - DiT-L/2, Euler-50, fp32 - but one step is a BOUNDED SAMPLE of it: REF_NFE_PER_STEP of the 50 Euler
+    network evaluations of a pass on REF_BATCH of the 64 latents (every NFE costs the same, so
+    images/s = REF_BATCH x NFE_run / (50 x step seconds)); the config object says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -203,25 +232,118 @@ def run_reference(args):
     from oracle import solvers as osol
     cfg = odit.make_config(MODEL, num_classes=1, label_dropout=0.0)
     sd = odit.synthetic_state_dict(cfg, WEIGHT_SEED)
-    B, nfe_s = 4, 10
+    B, nfe_s = REF_BATCH, REF_NFE_PER_STEP
     x = torch.randn(B, 4, 32, 32, generator=torch.Generator().manual_seed(0))
     f = lambda t, xx: odit.dit_forward(sd, cfg, t, xx)  # noqa: E731
-    for _ in range(max(1, args.warmup)):
-        osol.tdq_euler(f, x, 1.0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        osol.tdq_euler(f, x, 1.0 / nfe_s)
     t0 = time.time()
     for _ in range(args.steps):
         osol.tdq_euler(f, x, 1.0 / nfe_s)
     dt = (time.time() - t0) / args.steps
     value = B * nfe_s / dt / NFE
-    sample = f"each step = DiT-L/2 fp32, batch {B}, {nfe_s} Euler NFE on {threads} threads; images/s scaled to Euler-{NFE}"
+    sample = (f"each step = {nfe_s} of the {NFE} Euler NFE of one pass on {B} of the {BATCH} latents: DiT-L/2 fp32 oracle port, on "
+              f"{threads} host threads ({dt:.2f} s per step); images/s = {B} x {nfe_s} / (step time x {NFE})")
+    conf = workload_config(int(os.environ.get("WORLD_SIZE", "1")))
+    conf["workload"] = (f"{MODEL} 32x32x4 latents, Euler-{NFE} metric measured on a bounded sample: batch {B}, {nfe_s} Euler NFE per "
+                        f"step, fp32, host CPU ({threads} threads), rank 0 only; scaled to Euler-{NFE} images/s")
+    conf["global_batch"] = B
+    conf["reference_step"] = sample
     line = {"impl": "reference", "metric": "images/sec DiT-L/2 32x32 latents Euler-50", "value": value, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(int(os.environ.get("WORLD_SIZE", "1"))),
+            "config": conf,
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ extra legs
+
+FLOPS_DIT_L = 161_386_856_448   # algorithmic FLOPs per sample per NFE
+FLOPS_DIT_B = 46_003_912_704
+FLOPS_UNET_CELEB512 = 189.72e9
+
+
+def gemm_vs_cublas(device, iters=20):
+    """The four DiT-L/2 linear layers at batch 64 (M = 16384): our CTA-pair tcgen05 kernel WITH its fused epilogue
+    (bias / GELU / gated residual add) against the bare torch.matmul (cuBLAS) of the same operands on the same box, CUDA
+    events, alternating so that both see the same clocks.  ratio > 1: ours is faster."""
+    from lfm_b200 import _lib
+    lib = _lib.load()
+    s = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    M = BATCH * 256
+    out = {}
+    for name, N, K, epi in (("qkv", 3072, 1024, 0), ("proj", 1024, 1024, 2), ("fc1", 4096, 1024, 1), ("fc2", 1024, 4096, 2)):
+        a = torch.randn(M, K, device=device).bfloat16()
+        w = (torch.randn(N, K, device=device) * 0.03).bfloat16()
+        bias = torch.randn(N, device=device)
+        gate = torch.randn(M // 256, N, device=device)
+        o = torch.zeros(M, N, device=device, dtype=torch.float32 if epi >= 2 else torch.bfloat16)
+
+        def ours():
+            rc = lib.lfm_dbg_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), o.data_ptr(), gate.data_ptr(), N, 256, M, N, K, epi, 512, s)
+            assert rc == 0, _lib.last_error()
+
+        def cublas():
+            return a @ w.t()
+
+        def t(fn):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(device)
+            return e0.elapsed_time(e1) / iters * 1e3
+        us_o, us_c = [], []
+        for _ in range(3):
+            us_o.append(t(ours))
+            us_c.append(t(cublas))
+        uo, uc = min(us_o), min(us_c)
+        fl = 2.0 * M * N * K
+        out[name] = {"M": M, "N": N, "K": K, "ours_us": round(uo, 1), "cublas_us": round(uc, 1), "ours_tflops": round(fl / uo / 1e6, 1),
+                     "cublas_tflops": round(fl / uc / 1e6, 1), "ratio": round(uc / uo, 3)}
+        del a, w, o
+    return out
+
+
+def gpu_eager_baseline(device, nfe_run=10):
+    """The reference network in eager PyTorch on THIS GPU (tests/tools/eager_dit.py): the library baseline a user of the
+    reference gets on a B200 - bf16 autocast + F.scaled_dot_product_attention + TF32 on - and the reference's own
+    setting, fp32 with TF32 off (test_flow_latent.py:103).  Same weights, batch and Euler grid as the headline; a bounded
+    sample of nfe_run Euler steps scaled to Euler-50."""
+    from tests.tools import eager_dit
+    import lfm_b200
+    from lfm_b200.synthetic import synthetic_state_dict
+    with torch.device("meta"):
+        net = lfm_b200.DiT_models[MODEL](img_resolution=32, in_channels=4, label_dropout=0.0, num_classes=1)
+    sd = {k: v.to(device) for k, v in synthetic_state_dict(net, WEIGHT_SEED).items()}
+    arch = dict(depth=24, hidden=1024, heads=16)
+    x = torch.randn(BATCH, 4, 32, 32, device=device)
+    nodes = lfm_b200.euler_time_grid(STEP_SIZE)[: nfe_run + 1].to(device)
+    res = {}
+    for label, tf32, ac, n in (("bf16_autocast_sdpa_tf32", True, True, nfe_run), ("fp32_tf32_off", False, False, 2)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        nd = nodes[: n + 1]
+        eager_dit.euler(sd, x, nd[:2], autocast_bf16=ac, **arch)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eager_dit.euler(sd, x, nd, autocast_bf16=ac, **arch)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms_nfe = e0.elapsed_time(e1) / n
+        res[label] = {"ms_per_nfe": round(ms_nfe, 3), "images_per_s": round(BATCH / (ms_nfe * 1e-3) / NFE, 2),
+                      "tflops": round(BATCH * FLOPS_DIT_L / ms_nfe / 1e9, 1), "nfe_timed": n}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    res["what"] = f"eager PyTorch {torch.__version__} on this GPU, DiT-L/2 batch {BATCH}, Euler NFE scaled to Euler-{NFE} images/s"
+    return res
 
 
 def main():
@@ -231,6 +353,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_configs / gemm_vs_cublas / gpu_eager_baseline / decode")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -250,8 +373,8 @@ def main():
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     peaks = load_peaks()
-    net = build_model(device)
-    flops_nfe = 161_386_856_448  # algorithmic FLOPs per sample per NFE, DiT-L/2
+    net = build_model(device, max_batch=BATCH if args.no_extras else 128)   # 128: BASELINE.json configs[4] reuses this context
+    flops_nfe = FLOPS_DIT_L
     sargs = types.SimpleNamespace(method="euler", step_size=STEP_SIZE, perturb=False, cfg_scale=1.0, compute_nfe=False)
     chw = 4 * 32 * 32
 
@@ -277,10 +400,12 @@ def main():
         out_host.copy_(allx[rank::world] if world > 1 else allx, non_blocking=True)
         return allx
 
-    def timed(fn, k):
+    def timed(fn, k, counter=None):
+        """k calls of fn bracketed by barrier + synchronize; CUDA events; MAX over ranks (ms total)."""
+        counter = counter or net
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = net.launch_count()
+        l0 = counter.launch_count()
         e0.record()
         for _ in range(k):
             fn()
@@ -289,7 +414,7 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), net.launch_count() - l0
+        return float(ms.item()), counter.launch_count() - l0
 
     for _ in range(args.warmup):
         step_device()
@@ -302,11 +427,77 @@ def main():
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 
+    # ------------------------------------------------------------------ BASELINE.json configs 3, 4, 5 at this GPU count
+    other = {}
+    if not args.no_extras:
+        def sweep(per_gpu, nfes, reps=2):
+            x = torch.randn(per_gpu, 4, 32, 32, generator=torch.Generator().manual_seed(7 + rank)).to(device)
+            rows = []
+            for n in nfes:
+                a = types.SimpleNamespace(method="euler", step_size=1.0 / n, perturb=False, cfg_scale=1.0, compute_nfe=False)
+
+                def fn():
+                    xf = lfm_b200.sample_from_model(net, x, {}, a)[-1]
+                    return ldist.all_gather_batch(xf) if world > 1 else xf
+                fn()
+                ms, _ = timed(fn, reps)
+                ms /= reps
+                rows.append({"euler_nfe": n, "images_per_s": round(per_gpu * world / ms * 1e3, 2), "ms_per_pass": round(ms, 2),
+                             "tflops_per_gpu": round(n * per_gpu * FLOPS_DIT_L / ms / 1e9, 1)})
+            return rows
+        other["cfg5_weak"] = {"what": f"DiT-L/2 Euler NFE sweep, batch 128 per GPU (global {128 * world}), dp{world}",
+                              "rows": sweep(128, (10, 20, 50, 100))}
+        per = max(1, 128 // world)
+        other["cfg5_strong"] = {"what": f"DiT-L/2 Euler NFE sweep, GLOBAL batch 128 => {per} per GPU (M = {per * 256} token rows), dp{world}",
+                                "rows": sweep(per, (10, 20, 50, 100)) if world > 1 else "identical to cfg5_weak at 1 GPU"}
+    del net
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        # cfg3: DiT-B/2, 1000 classes, CFG 1.5, Karras Heun-25 (48 NFE, 2 network rows per image), 32 images per GPU
+        nb = build_model(device, "DiT-B/2", 1000, 0.1, 64)
+        gg = torch.Generator().manual_seed(11 + rank)
+        xb = torch.randn(32, 4, 32, 32, generator=gg).to(device)
+        yb = torch.randint(0, 1000, (32,), generator=gg).to(device)
+        mk = dict(y=torch.cat([yb, torch.full((32,), 1000, device=device)]), cfg_scale=1.5)
+
+        def fn3():
+            out = lfm_b200.karras_sample(nb, torch.cat([xb, xb]), 25, clip_denoised=False, model_kwargs=mk, sigma_min=1e-5,
+                                         sigma_max=1.0, sampler="heun")[:32]
+            return ldist.all_gather_batch(out) if world > 1 else out
+        fn3()
+        ms, _ = timed(fn3, 3, nb)
+        ms /= 3
+        nfe3 = nb.last_stats["nfe"]
+        other["cfg3"] = {"what": f"DiT-B/2 imnet, CFG 1.5, Heun-25 ({nfe3} NFE x 2 rows), 32 images per GPU (global {32 * world}), dp{world}",
+                         "images_per_s": round(32 * world / ms * 1e3, 2), "ms_per_pass": round(ms, 2),
+                         "tflops_per_gpu": round(nfe3 * 64 * FLOPS_DIT_B / ms / 1e9, 1)}
+        del nb
+        torch.cuda.empty_cache()
+        if world == 1:
+            # cfg4: ADM UNetModel celeb512 (64x64x4 latents), dopri5 atol = rtol = 1e-5, batch 32, one GPU
+            nu = build_unet_celeb512(device, 32)
+            xu = torch.randn(32, 4, 64, 64, generator=torch.Generator().manual_seed(13)).to(device)
+            a4 = types.SimpleNamespace(method="dopri5", atol=1e-5, rtol=1e-5, cfg_scale=1.0, compute_nfe=True)
+            fn4 = lambda: lfm_b200.sample_from_model(nu, xu, {}, a4)  # noqa: E731
+            fn4()
+            ms, _ = timed(fn4, 2, nu)
+            ms /= 2
+            st = nu.last_stats
+            other["cfg4"] = {"what": "ADM UNetModel celeb512 preset, dopri5 atol=rtol=1e-5, batch 32, 1 GPU", **st,
+                             "images_per_s": round(32 / ms * 1e3, 2), "ms_per_pass": round(ms, 2),
+                             "tflops_per_gpu": round(st["nfe"] * 32 * FLOPS_UNET_CELEB512 / ms / 1e9, 1)}
+            del nu
+            torch.cuda.empty_cache()
+
     if rank == 0:
         imgs = BATCH * world * args.steps
         value = imgs / (ms_total * 1e-3)
         e2e_value = imgs / (ms_e2e * 1e-3)
         tflops = value * NFE * flops_nfe / 1e12 / world  # per GPU
+        extras = {}
+        if world == 1 and not args.no_extras:
+            extras["gpu_eager_baseline"] = gpu_eager_baseline(device)
+            extras["gemm_vs_cublas"] = gemm_vs_cublas(device)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = usable_threads()
@@ -336,6 +527,9 @@ def main():
             line["roofline"] = roof
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if other:
+            line["other_configs"] = other
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -98,3 +98,17 @@ def test_pos_embed_spots():
 def test_flop_formula():
     assert odit.dit_flops_per_sample(odit.make_config("DiT-L/2")) == 161_386_856_448
     assert odit.dit_flops_per_sample(odit.make_config("DiT-B/2")) == 46_003_912_704
+
+
+def test_eager_baseline_restatement_matches_reference_fixture():
+    """tests/tools/eager_dit.py (the plain-PyTorch SDPA baseline bench.py times on the GPU) computes the reference's
+    DiT: checked here on the CPU against the reference-generated fixture, so the baseline is a fair one."""
+    from tests.tools import eager_dit
+    g = load_golden("mini_cond")
+    cfg = cfg_from_golden(g)
+    sd = odit.synthetic_state_dict(cfg, int(g["weight_seed"]))
+    arch = dict(depth=cfg.depth, hidden=cfg.hidden_size, heads=cfg.num_heads)
+    v = eager_dit.dit_forward(sd, T(g["t_vec"]), T(g["x"]), T(g["y"]), **arch)
+    assert rel_l2(v, g["v_vec_y"]) < 1e-5
+    v = eager_dit.dit_forward(sd, T(g["t_scalar"]), T(g["x"]), None, **arch)
+    assert rel_l2(v, g["v_scalar_ynone"]) < 1e-5
