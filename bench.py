@@ -429,7 +429,36 @@ def main():
 
     # ------------------------------------------------------------------ BASELINE.json configs 3, 4, 5 at this GPU count
     other = {}
+    decode = None
     if not args.no_extras:
+        # ---- images/s INCLUDING the VAE decode (test_flow_latent.py:193): native decoder, synthetic weights, the uint8
+        # post-processing fused, and the one all-gather moving the DECODED images (196 KB each) as north_star says
+        from lfm_b200.vae import AutoencoderKL, synthetic_vae_state_dict
+        vae = AutoencoderKL(max_batch=16)
+        vae.load_state_dict(synthetic_vae_state_dict(vae, WEIGHT_SEED), strict=True)
+        vae = vae.to(device).eval()
+
+        def step_decode():
+            xf = lfm_b200.sample_from_model(net, z_dev, {}, sargs)[-1]
+            u8 = vae.decode_to_uint8(xf / 0.18215)
+            return ldist.all_gather_batch(u8) if world > 1 else u8
+        xf0 = step_device()[:BATCH].contiguous()
+        step_decode()
+        ms_sd, _ = timed(step_decode, 3)
+        ms_sd /= 3
+        fn_d = lambda: vae.decode_to_uint8(xf0 / 0.18215)  # noqa: E731
+        fn_d()
+        ms_d, _ = timed(fn_d, 3, vae)
+        ms_d /= 3
+        fl = AutoencoderKL().decode_flops_per_image(32)
+        decode = {"what": f"Euler-{NFE} sampling + native AutoencoderKL decode (256x256, synthetic sd-vae-ft-mse-shaped weights) + uint8 "
+                          f"post-processing, batch {BATCH}/GPU; all-gather of the decoded uint8 images for N > 1",
+                  "images_per_s_with_decode": round(BATCH * world / ms_sd * 1e3, 2), "ms_per_pass": round(ms_sd, 2),
+                  "decode_only_ms_per_batch": round(ms_d, 2), "decode_only_images_per_s_per_gpu": round(BATCH / ms_d * 1e3, 1),
+                  "decode_tflops_per_gpu": round(BATCH * fl / ms_d / 1e9, 1), "decode_flops_per_image": fl}
+        del vae
+        torch.cuda.empty_cache()
+
         def sweep(per_gpu, nfes, reps=2):
             x = torch.randn(per_gpu, 4, 32, 32, generator=torch.Generator().manual_seed(7 + rank)).to(device)
             rows = []
@@ -527,6 +556,8 @@ def main():
             line["roofline"] = roof
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if decode is not None:
+            line["decode"] = decode
         if other:
             line["other_configs"] = other
         line.update(extras)

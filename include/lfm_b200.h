@@ -77,6 +77,21 @@ typedef struct lfm_edm_desc {
     int32_t attn_resolutions[8];  /* feature-map RESOLUTIONS with self-attention (EDM.py:788) */
 } lfm_edm_desc;
 
+/* Decoder half of the Stable-Diffusion AutoencoderKL the reference loads with
+ * AutoencoderKL.from_pretrained(args.pretrained_autoencoder_ckpt) (test_flow_latent.py:131, test_flow_latent_ddp.py:57;
+ * "stabilityai/sd-vae-ft-mse": block_out_channels (128, 256, 512, 512), layers_per_block 2, norm_num_groups 32,
+ * latent_channels 4, out_channels 3).  diffusers is a third-party dependency outside /root/reference: the architecture
+ * is restated in oracle/vae.py (parity unpinned). */
+typedef struct lfm_vae_desc {
+    int32_t latent_size;            /* latent side = image_size // 8: 16, 32 (256 x 256 images; the LFM presets) */
+    int32_t latent_channels;        /* 4 */
+    int32_t out_channels;           /* 3 */
+    int32_t n_blocks;               /* number of entries used in block_out_channels */
+    int32_t block_out_channels[8];  /* encoder order, e.g. 128, 256, 512, 512 (the decoder walks it backwards) */
+    int32_t layers_per_block;       /* 2 => 3 ResnetBlock2D per decoder up-block */
+    int32_t norm_num_groups;        /* 32 */
+} lfm_vae_desc;
+
 typedef struct lfm_ode_stats {
     int64_t nfe;       /* network evaluations */
     int64_t accepted;  /* dopri5 accepted steps */
@@ -99,6 +114,19 @@ int lfm_create_unet(const lfm_unet_desc* desc, int device, lfm_ctx** out);
  * State-dict keys as in the reference, including the constant `*.resample_filter` buffers of the up/down blocks
  * (accepted and checked to be 0.25). */
 int lfm_create_edm(const lfm_edm_desc* desc, int device, lfm_ctx** out);
+
+/* AutoencoderKL.from_pretrained(...) (test_flow_latent.py:131): a context for the DECODER.  lfm_set_param takes the
+ * `decoder.*` and `post_quant_conv.*` entries of the diffusers state dict (attention projections under their current
+ * names to_q / to_k / to_v / to_out.0); lfm_finalize(max_batch) sizes the workspace for max_batch images per call. */
+int lfm_create_vae(const lfm_vae_desc* desc, int device, lfm_ctx** out);
+
+/* first_stage_model.decode(z).sample (test_flow_latent.py:193, test_flow_latent_ddp.py:110; the caller divides the
+ * latents by scale_factor as the reference does) and, optionally, the post-processing of the generation loop
+ * (test_flow_latent_ddp.py:131-135) fused into the decoder's last kernel:
+ *   z:       [B, 4, s, s] fp32 NCHW (device)
+ *   out_f32: [B, 3, 8s, 8s] fp32 NCHW `sample`, or NULL
+ *   out_u8:  [B, 8s, 8s, 3] uint8 = (clamp((sample + 1) / 2, 0, 1) * 255).permute(0, 2, 3, 1).to(uint8), or NULL */
+int lfm_decode(lfm_ctx* ctx, const float* z, int B, float* out_f32, uint8_t* out_u8, void* stream);
 
 /* nn.Module.load_state_dict (test_flow_latent.py:142): one call per state-dict entry, `key` exactly as in the
  * reference state_dict; `ptr` may be a host or a device pointer (fp32).  The data is copied
@@ -152,7 +180,7 @@ int64_t lfm_launch_count(const lfm_ctx* ctx);
 int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float* bias, void* out, const float* gate,
                  int gate_stride, int rows_per_sample, int M, int N, int K, int epi, int block_n, void* stream);
 /* softmax(q k^T / 8) v on a [B*256, 3*D] bf16 qkv buffer -> out [B*256, D] bf16.  variant: 3 = persistent single-TMEM-read kernel (default), 2 = persistent two-pass, 0 = P in TMEM,
- * 1 = P through shared memory, 4 = EXPERIMENTAL two-warpgroups-per-tile kernel (attention4.cuh; not part of the tested set).  dbg_s (optional) receives the raw S = q k^T as fp32 [B, H, 256, 256]. */
+ * 1 = P through shared memory, 5 = version 3 with one MMA issuer thread per query tile ("ping-pong", attention5.cuh).  dbg_s (optional) receives the raw S = q k^T as fp32 [B, H, 256, 256]. */
 int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, int H, int variant, float* dbg_s, void* stream);
 /* Intermediate activations of the last lfm_forward (fp32 token stream [B*T, D] after all blocks). */
 int lfm_dbg_tokens(lfm_ctx* ctx, float* out, int B);

@@ -28,6 +28,12 @@ class EdmDesc(C.Structure):
                 ("attn_resolutions", C.c_int32 * 8)]
 
 
+class VaeDesc(C.Structure):
+    _fields_ = [("latent_size", C.c_int32), ("latent_channels", C.c_int32), ("out_channels", C.c_int32),
+                ("n_blocks", C.c_int32), ("block_out_channels", C.c_int32 * 8), ("layers_per_block", C.c_int32),
+                ("norm_num_groups", C.c_int32)]
+
+
 class OdeStats(C.Structure):
     _fields_ = [("nfe", C.c_int64), ("accepted", C.c_int64), ("rejected", C.c_int64)]
 
@@ -38,6 +44,8 @@ SYMBOLS = {
     "lfm_create": (C.c_int, [C.POINTER(ModelDesc), C.c_int, C.POINTER(_P)]),
     "lfm_create_unet": (C.c_int, [C.POINTER(UnetDesc), C.c_int, C.POINTER(_P)]),
     "lfm_create_edm": (C.c_int, [C.POINTER(EdmDesc), C.c_int, C.POINTER(_P)]),
+    "lfm_create_vae": (C.c_int, [C.POINTER(VaeDesc), C.c_int, C.POINTER(_P)]),
+    "lfm_decode": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "lfm_set_param": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "lfm_finalize": (C.c_int, [_P, C.c_int]),
     "lfm_forward": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_float, _P, _P]),

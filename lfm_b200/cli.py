@@ -14,7 +14,12 @@ Differences, all deliberate:
   * the Karras path works (the reference's CLI raises NameError / TypeError there);
   * ``--device`` exists; nothing is hard-coded to "cuda";
   * ``--synthetic_init SEED`` runs without a checkpoint (seeded non-degenerate weights);
-  * without ``diffusers`` (not in this image) the VAE decode is skipped and latents are saved (``--no_decode``).
+  * the VAE decode runs natively (lfm_b200.AutoencoderKL: ``--pretrained_autoencoder_ckpt`` = a LOCAL diffusers
+    directory, or ``--synthetic_vae SEED``); ``--vae diffusers`` keeps the reference's torch module when that package is
+    installed; with neither, latents are saved (``--no_decode``);
+  * in the generation loop (``--compute_fid``) the post-processing (clamp -> uint8 -> NHWC) is fused into the native
+    decoder, the images leave the GPU through pinned buffers asynchronously and a thread pool encodes the JPEGs, so the
+    GPU does not wait for PIL (the reference encodes on the main thread, test_flow_latent_ddp.py:131-139).
 """
 from __future__ import annotations
 
@@ -86,6 +91,10 @@ def build_parser():
     p.add_argument("--device", type=str, default=None, help="cuda:N (default: cuda:LOCAL_RANK)")
     p.add_argument("--synthetic_init", type=int, default=None, metavar="SEED", help="seeded weights instead of a checkpoint")
     p.add_argument("--no_decode", action="store_true", help="skip the VAE decode; save latents (.npy)")
+    p.add_argument("--vae", type=str, default="native", choices=["native", "diffusers"],
+                   help="native: lfm_b200.AutoencoderKL (sm_100a kernels); diffusers: the reference's torch module")
+    p.add_argument("--synthetic_vae", type=int, default=None, metavar="SEED", help="seeded decoder weights instead of a checkpoint")
+    p.add_argument("--writer_threads", type=int, default=8, help="JPEG encoder threads of the --compute_fid loop")
     p.add_argument("--out_dir", type=str, default=".")
     p.add_argument("--measure_reps", type=int, default=300)
     return p
@@ -112,22 +121,82 @@ def load_model(args, device):
 
 
 def load_vae(args, device):
+    """test_flow_latent.py:131 ``AutoencoderKL.from_pretrained(args.pretrained_autoencoder_ckpt).to(device)``."""
     if args.no_decode:
         return None
-    try:
-        from diffusers.models import AutoencoderKL
-    except ImportError:
-        print("diffusers is not installed: skipping the VAE decode, saving latents instead (--no_decode)")
-        args.no_decode = True
-        return None
-    return AutoencoderKL.from_pretrained(args.pretrained_autoencoder_ckpt).to(device)
+    if args.vae == "diffusers":
+        try:
+            from diffusers.models import AutoencoderKL as TorchVAE
+        except ImportError:
+            raise SystemExit("--vae diffusers: the diffusers package is not installed (use the native decoder)")
+        return TorchVAE.from_pretrained(args.pretrained_autoencoder_ckpt).to(device)
+    from .vae import AutoencoderKL, synthetic_vae_state_dict
+    if args.synthetic_vae is not None:
+        vae = AutoencoderKL()
+        vae.load_state_dict(synthetic_vae_state_dict(vae, args.synthetic_vae), strict=True)
+        return vae.to(device).eval()
+    if os.path.isdir(args.pretrained_autoencoder_ckpt):
+        return AutoencoderKL.from_pretrained(args.pretrained_autoencoder_ckpt).to(device)
+    print(f"'{args.pretrained_autoencoder_ckpt}' is not a local diffusers directory (no hub access here) and no "
+          "--synthetic_vae seed was given: skipping the VAE decode, saving latents instead (--no_decode)")
+    args.no_decode = True
+    return None
+
+
+class ImageSink:
+    """Device -> pinned host -> JPEG files without stalling the sampler (test_flow_latent_ddp.py:131-139 does
+    ``.to("cpu")`` + ``Image.fromarray(x).save`` per image on the main thread).  ``put`` enqueues an asynchronous D2H
+    copy of a uint8 NHWC batch on a side stream and returns; a pool of encoder threads waits for the copy's event and
+    writes the files.  Two pinned buffers alternate: the sampler is blocked only if it runs two batches ahead."""
+
+    def __init__(self, device, threads=8):
+        from concurrent.futures import ThreadPoolExecutor
+        self.device = device
+        self.pool = ThreadPoolExecutor(max_workers=max(1, threads))
+        self.copy_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.bufs, self.pending, self.turn = [None, None], [[], []], 0
+
+    def put(self, u8, paths):
+        i = self.turn
+        self.turn ^= 1
+        for f in self.pending[i]:          # the buffer's previous batch must be on disk before it is overwritten
+            f.result()
+        if self.bufs[i] is None or self.bufs[i].shape != u8.shape:
+            self.bufs[i] = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=self.device.type == "cuda")
+        host = self.bufs[i]
+        if self.copy_stream is not None:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(ready)
+                host.copy_(u8, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self.copy_stream)
+            u8.record_stream(self.copy_stream)
+        else:
+            host.copy_(u8)
+            done = None
+        arr = host.numpy()
+
+        def write(j, path):
+            if done is not None:
+                done.synchronize()
+            from PIL import Image
+            Image.fromarray(arr[j]).save(path)
+        self.pending[i] = [self.pool.submit(write, j, pth) for j, pth in enumerate(paths)]
+
+    def close(self):
+        for lst in self.pending:
+            for f in lst:
+                f.result()
+        self.pool.shutdown(wait=True)
 
 
 def make_run_sampling(args, model, vae, device):
     """test_flow_latent.py:161-194 / test_flow_latent_ddp.py:83-111."""
     from .solvers import sample_from_model, sample_from_model_with_fixed_step_solver
 
-    def run_sampling(num_samples, generator, cls_index=None, return_nfe=False):
+    def run_sampling(num_samples, generator, cls_index=None, return_nfe=False, as_uint8=False):
         side = args.image_size // 8
         x = generator.randn(num_samples, 4, side, side).to(device)
         if args.num_classes in [None, 1]:
@@ -157,6 +226,8 @@ def make_run_sampling(args, model, vae, device):
             fake_sample, _ = fake_sample.chunk(2, dim=0)
         if vae is None:
             result = fake_sample
+        elif as_uint8 and hasattr(vae, "decode_to_uint8"):
+            result = vae.decode_to_uint8(fake_sample / args.scale_factor)     # [n, H, W, 3] uint8, post-processing fused
         else:
             result = vae.decode(fake_sample / args.scale_factor).sample
         return (result, nfe) if return_nfe else result
@@ -225,27 +296,30 @@ def main(argv=None):
         if world > 1:
             torch.distributed.barrier()
         total = 0
+        sink = ImageSink(device, args.writer_threads) if vae is not None else None
         for i in range(iters):
-            out = run_sampling(n, generator)
+            out = run_sampling(n, generator, as_uint8=True)
             if vae is None:
                 for j, z in enumerate(out):
                     np.save("{}/{}.npy".format(save_dir, ldist.file_index(j, world, rank, total)), z.cpu().numpy())
             else:
-                import torchvision
-                img = torch.clamp((out + 1.0) / 2.0, 0, 1)
-                for j, im in enumerate(img):
-                    torchvision.utils.save_image(im, "{}/{}.jpg".format(save_dir, ldist.file_index(j, world, rank, total)))
+                if out.dtype != torch.uint8:      # the torch VAE: the reference's expression (test_flow_latent_ddp.py:131-135)
+                    out = (torch.clamp((out + 1.0) / 2.0, 0, 1) * 255.0).permute(0, 2, 3, 1).to(torch.uint8)
+                sink.put(out, ["{}/{}.jpg".format(save_dir, ldist.file_index(j, world, rank, total)) for j in range(out.shape[0])])
             total += n * world
             if rank == 0:
                 print("generating batch ", i)
+        if sink is not None:
+            sink.close()
         if world > 1:
             torch.distributed.barrier()
         if rank == 0:
             print("samples written to", save_dir, "- run the reference's pytorch_fid on them for the FID statistic")
         return 0
 
-    # default: one batch; every rank samples its shard and ONE all-gather assembles the result on all ranks
-    out = run_sampling(args.batch_size, generator)
+    # default: one batch; every rank samples (and decodes) its shard and ONE all-gather assembles the result on all
+    # ranks - of the decoded uint8 images when the native decoder runs (196 KB per 256 x 256 image), else of the latents
+    out = run_sampling(args.batch_size, generator, as_uint8=True)
     out = ldist.all_gather_batch(out)
     if rank == 0:
         if args.use_karras_samplers:
@@ -261,7 +335,8 @@ def main(argv=None):
         else:
             import torchvision
             path = os.path.join(args.out_dir, stem + ".jpg")
-            torchvision.utils.save_image(torch.clamp((out + 1.0) / 2.0, 0, 1), path, padding=0, nrow=8)
+            img = out.permute(0, 3, 1, 2).float() / 255.0 if out.dtype == torch.uint8 else torch.clamp((out + 1.0) / 2.0, 0, 1)
+            torchvision.utils.save_image(img, path, padding=0, nrow=8)
         print("Samples are save at '{}".format(path))
     if world > 1:
         torch.distributed.barrier()

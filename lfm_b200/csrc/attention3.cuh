@@ -25,6 +25,25 @@
 
 namespace lfm {
 
+// max of three (one FMNMX3 on sm_100)
+LFM_DEVICE float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// Row maximum of 128 fp32 values held as 4 x 32 registers: eight independent 3-input chains (a serial fmaxf chain
+// costs 128 dependent instructions of a warp that has nothing else to issue until the maximum is known).
+LFM_DEVICE float row_max128(const uint32_t (*v)[32]) {
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = fmaxf(__uint_as_float(v[k >> 1][(k & 1) * 16]), __uint_as_float(v[k >> 1][(k & 1) * 16 + 1]));
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 2; j < 16; j += 2)
+            m[k] = fmax3(m[k], __uint_as_float(v[k >> 1][(k & 1) * 16 + j]), __uint_as_float(v[k >> 1][(k & 1) * 16 + j + 1]));
+    return fmaxf(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], fmax3(m[5], m[6], m[7])));
+}
 
 __global__ void __launch_bounds__(kA2Threads, 1)
 attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D] bf16, box {64, 256}
@@ -149,18 +168,15 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
             mbar_wait(&s_full[g], hp);
             tc_fence_after();
             // one half (128 keys) at a time: the half's S values live in registers, are read from TMEM once
-            float mAs, mBs, sumA = 0.f, sumB = 0.f;
+            float mAs, mBs, sumA, sumB;
             {
                 uint32_t v[4][32];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(taddr + c * 32, v[c]);
                 tmem_ld_wait();
-                float mx = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[c][j]));
+                const float mx = row_max128(v);
                 mAs = mx * scale_log2e;
+                float sacc[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial sums: no serial FADD chain behind the MUFU pipe
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
@@ -168,11 +184,12 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
                     for (int j = 0; j < 16; ++j) {
                         const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j]), scale_log2e, -mAs));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j + 1]), scale_log2e, -mAs));
-                        sumA += p0 + p1;
+                        sacc[j & 3] += p0 + p1;
                         pk[j] = pack_bf16x2(p0, p1);
                     }
                     tmem_st_32x32b_x16(taddr + c * 16, pk);  // P_A -> cols [0,64) (S_A is already in registers)
                 }
+                sumA = (sacc[0] + sacc[1]) + (sacc[2] + sacc[3]);
             }
             {
                 uint32_t v[4][32];
@@ -182,12 +199,9 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
                 tmem_st_wait();   // P_A visible
                 tc_fence_before();
                 mbar_arrive(&p_full[g]);
-                float mx = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[c][j]));
+                const float mx = row_max128(v);
                 mBs = mx * scale_log2e;
+                float sacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
@@ -195,11 +209,12 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
                     for (int j = 0; j < 16; ++j) {
                         const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j]), scale_log2e, -mBs));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j + 1]), scale_log2e, -mBs));
-                        sumB += p0 + p1;
+                        sacc[j & 3] += p0 + p1;
                         pk[j] = pack_bf16x2(p0, p1);
                     }
                     tmem_st_32x32b_x16(taddr + 64 + c * 16, pk);  // P_B -> cols [64,128)
                 }
+                sumB = (sacc[0] + sacc[1]) + (sacc[2] + sacc[3]);
             }
             tmem_st_wait();
             tc_fence_before();

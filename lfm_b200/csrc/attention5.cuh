@@ -160,11 +160,7 @@ attention5_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(taddr + c * 32, v[c]);
                 tmem_ld_wait();
-                float mx = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[c][j]));
+                const float mx = row_max128(v);
                 mAs = mx * scale_log2e;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -187,11 +183,7 @@ attention5_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
                 tmem_st_wait();   // P_A visible
                 tc_fence_before();
                 mbar_arrive(&p_full[g]);
-                float mx = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[c][j]));
+                const float mx = row_max128(v);
                 mBs = mx * scale_log2e;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {

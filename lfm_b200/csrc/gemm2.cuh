@@ -64,14 +64,21 @@ LFM_DEVICE void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* 
 }
 
 // Implicit-GEMM convolution geometry (taps == 0: plain GEMM, A is a 2-D [M, K] matrix).
-// Output pixels are flattened (b, h, w) row-major; a CTA's 128 output rows are whole image rows (W * rows == 128)
-// or whole images (H * W divides 128), so the matching input window of tap (r, s) is ONE 4-D box.
+// Output pixels are flattened (b, h, w) row-major; a CTA's 128 output rows are whole image rows (W * rows == 128),
+// whole images (H * W divides 128) or one 128-pixel segment of an image row (W = 256: the VAE decoder's last stage),
+// so the matching input window of tap (r, s) is ONE 4-D box.
 struct ConvGeom {
     int taps;     // 0 (GEMM), 9 (3x3, pad 1)
     int cblocks;  // C_in / 64
     int W;        // OUTPUT width
     int HW;       // OUTPUT height * width
     int stride;   // 1 or 2 (the tensor map carries the matching element strides)
+    // Batched GEMM (taps == 0, batch_m > 0): the M rows are batch_m-row groups; group g multiplies against ITS OWN
+    // block of W rows, [g * b_batch_rows, g * b_batch_rows + N)  - e.g. S_g = Q_g K_g^T per image.  a_mod > 0: the A
+    // operand is shared by all groups (A row = row % a_mod) - e.g. V_g^T = W_v X_g^T.  batch_m % 256 == 0, N % 256 == 0.
+    int batch_m = 0;
+    int a_mod = 0;
+    int b_batch_rows = 0;
 };
 
 LFM_DEVICE void umma_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -308,13 +315,16 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 int m_blk, n_blk, nh, width;
                 decode(item, m_blk, n_blk, nh, width);
                 const bool halfw = width != kG2BlockN;
-                const int row_a = m_blk * 256 + static_cast<int>(rank) * 128;
-                const int row_b = n_blk * kG2BlockN + nh * (kG2BlockN / 2) + static_cast<int>(rank) * (width / 2);
+                const int row_v = m_blk * 256 + static_cast<int>(rank) * 128;  // row of the output this CTA computes
+                const int row_a = cg.a_mod > 0 ? row_v % cg.a_mod : row_v;
+                const int row_b = (cg.batch_m > 0 ? (row_v / cg.batch_m) * cg.b_batch_rows : 0) + n_blk * kG2BlockN +
+                                  nh * (kG2BlockN / 2) + static_cast<int>(rank) * (width / 2);
                 const uint32_t tx_bytes = 2 * (kG2ABytes + (halfw ? kG2BBytes / 2 : kG2BBytes));
-                int img0 = 0, h0 = 0;
+                int img0 = 0, h0 = 0, w0 = 0;
                 if (cg.taps != 0) {
                     img0 = row_a / cg.HW;
                     h0 = (row_a % cg.HW) / cg.W;
+                    w0 = row_a % cg.W;  // non-zero only when an image row is wider than the 128-pixel tile (W = 256)
                 }
                 const int ks = ksplit > 1 ? item % ksplit : 0;
                 const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
@@ -330,7 +340,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                         tma_load_2d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * 64, row_a);
                     } else {
                         const int r = tap / 3, sx = tap - 3 * r;
-                        tma_load_4d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], cb * 64, sx - 1,
+                        tma_load_4d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], cb * 64, cg.stride * w0 + sx - 1,
                                         cg.stride * h0 + r - 1, img0);
                         if (++cb == cg.cblocks) {
                             cb = 0;

@@ -23,6 +23,7 @@
 #include "gemm4.cuh"
 #include "kernels.cuh"
 #include "unet.cuh"
+#include "vae.cuh"
 
 using namespace lfm;
 
@@ -686,7 +687,10 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
         ctx->launches++;                              \
     } while (0)
 
+static int check_ready(lfm_ctx* ctx, int rows, const char* who);
+
 #include "unet_host.inc"
+#include "vae_host.inc"
 
 static int ctx_unet_variant(const lfm_ctx* ctx) { return ctx->un != nullptr ? ctx->un->variant : 0; }
 

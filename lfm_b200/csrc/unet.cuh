@@ -93,6 +93,7 @@ struct GnApplyArgs {
     const float* film;  // nullptr, or per-sample [scale(C) | shift(C)] at film + b * film_stride
     int film_stride;
     int act;            // 0 none, 1 SiLU
+    float eps;          // 1e-5 (nn.GroupNorm default: ADM / EDM), 1e-6 (VAE decoder)
     __nv_bfloat16* out;
     float* copy_out;            // nullptr or fp32 [B, HW, C]
     __nv_bfloat16* raw_out;     // nullptr or bf16 [B, HW, C]
@@ -124,7 +125,7 @@ gn_apply_kernel(GnApplyArgs a) {
         double var = Q / n - mean * mean;
         if (var < 0.0) var = 0.0;
         s_mean[threadIdx.x] = static_cast<float>(mean);
-        s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+        s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
     }
     __syncthreads();
     const float* film = a.film != nullptr ? a.film + static_cast<size_t>(b) * a.film_stride : nullptr;

@@ -161,29 +161,49 @@ def _gn(x, w, b):
     return F.group_norm(x.float(), 32, w, b, eps=1e-5)
 
 
+# Optional emulation of the CUDA path's operand rounding (unet_forward(..., emulate_bf16=True)): the operands of every
+# tensor-core contraction (3x3 / 1x1 convolutions, qkv / proj) are rounded to bf16, accumulation stays fp32.  Used ONLY
+# to give the adaptive solver's oracle run the same noise floor in v as the native path (tests/test_gpu_parity.py,
+# cfg4): the embedded error estimate of dopri5 at rtol = 1e-5 is dominated by that noise, so the step count of an
+# fp32 run is not comparable.  The default (False) is the plain fp32 restatement that the fixtures pin.
+_EMULATE_BF16 = False
+
+
+def _r(t):
+    return t.bfloat16().float() if _EMULATE_BF16 else t
+
+
+def _conv2d(x, w, b, **kw):
+    return F.conv2d(_r(x), _r(w), b, **kw)
+
+
+def _conv1d(x, w, b):
+    return F.conv1d(_r(x), _r(w), b)
+
+
 def _res(sd, p, x, emb):
-    h = F.conv2d(F.silu(_gn(x, sd[p + "in_layers.0.weight"], sd[p + "in_layers.0.bias"])),
-                 sd[p + "in_layers.2.weight"], sd[p + "in_layers.2.bias"], padding=1)
+    h = _conv2d(F.silu(_gn(x, sd[p + "in_layers.0.weight"], sd[p + "in_layers.0.bias"])),
+                sd[p + "in_layers.2.weight"], sd[p + "in_layers.2.bias"], padding=1)
     e = F.linear(F.silu(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"])[..., None, None]
     scale, shift = torch.chunk(e, 2, dim=1)            # unet.py:232 - scale first
     h = _gn(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"]) * (1 + scale) + shift
-    h = F.conv2d(F.silu(h), sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"], padding=1)
+    h = _conv2d(F.silu(h), sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"], padding=1)
     if p + "skip_connection.weight" in sd:
-        x = F.conv2d(x, sd[p + "skip_connection.weight"], sd[p + "skip_connection.bias"])
+        x = _conv2d(x, sd[p + "skip_connection.weight"], sd[p + "skip_connection.bias"])
     return x + h
 
 
 def _attn(sd, p, x, heads):
     b, c, hh, ww = x.shape
     xf = x.reshape(b, c, -1)
-    qkv = F.conv1d(_gn(xf, sd[p + "norm.weight"], sd[p + "norm.bias"]), sd[p + "qkv.weight"], sd[p + "qkv.bias"])
+    qkv = _r(_conv1d(_gn(xf, sd[p + "norm.weight"], sd[p + "norm.bias"]), sd[p + "qkv.weight"], sd[p + "qkv.bias"]))
     ch = c // heads
     q, k, v = qkv.reshape(b * heads, ch * 3, hh * ww).split(ch, dim=1)
     scale = 1 / math.sqrt(math.sqrt(ch))
     w = torch.einsum("bct,bcs->bts", q * scale, k * scale)
     w = torch.softmax(w.float(), dim=-1)
     a = torch.einsum("bts,bcs->bct", w, v).reshape(b, -1, hh * ww)
-    h = F.conv1d(a, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
+    h = _conv1d(a, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
     return (xf + h).reshape(b, c, hh, ww)
 
 
@@ -197,16 +217,23 @@ def _run_layers(sd, prefix, layers, h, emb):
         elif L[0] == "attn":
             h = _attn(sd, p, h, L[2])
         elif L[0] == "down":
-            h = F.conv2d(h, sd[p + "op.weight"], sd[p + "op.bias"], stride=2, padding=1)
+            h = _conv2d(h, sd[p + "op.weight"], sd[p + "op.bias"], stride=2, padding=1)
         elif L[0] == "up":
             h = F.interpolate(h, scale_factor=2, mode="nearest")
-            h = F.conv2d(h, sd[p + "conv.weight"], sd[p + "conv.bias"], padding=1)
+            h = _conv2d(h, sd[p + "conv.weight"], sd[p + "conv.bias"], padding=1)
     return h
 
 
 @torch.no_grad()
-def unet_forward(sd, cfg: UNetConfig, t, x, y=None):
+def unet_forward(sd, cfg: UNetConfig, t, x, y=None, emulate_bf16: bool = False):
     """v = UNetModel(t, x, y)  (unet.py:613-655).  t: 0-d (expanded to [B], :629-630) or [B]."""
+    global _EMULATE_BF16
+    if emulate_bf16:
+        _EMULATE_BF16 = True
+        try:
+            return unet_forward(sd, cfg, t, x, y)
+        finally:
+            _EMULATE_BF16 = False
     t = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
     if t.numel() != x.shape[0]:
         t = t * torch.ones(x.shape[0])
@@ -227,7 +254,7 @@ def unet_forward(sd, cfg: UNetConfig, t, x, y=None):
         h = torch.cat([h, hs.pop()], dim=1)
         h = _run_layers(sd, f"output_blocks.{i}", layers, h, emb)
     h = F.silu(_gn(h, sd["out.0.weight"], sd["out.0.bias"]))
-    return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
+    return _conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
 
 
 def unet_flops_per_sample(cfg: UNetConfig) -> int:

@@ -1,0 +1,212 @@
+"""Oracle: the decoder half of the Stable-Diffusion ``AutoencoderKL`` (TEST INFRASTRUCTURE; PARITY UNPINNED).
+
+The reference calls ``first_stage_model.decode(fake_sample / args.scale_factor).sample`` with
+``AutoencoderKL.from_pretrained("stabilityai/sd-vae-ft-mse")`` (test_flow_latent.py:131,193,360;
+test_flow_latent_ddp.py:57,110).  ``diffusers`` is a third-party dependency (requirements.txt:2, unpinned) that is
+neither in /root/reference nor in the build image, and the checkpoint is a network download - so neither the module
+nor golden vectors from it can be obtained here: this file RESTATES the published architecture (diffusers
+``models/autoencoders/autoencoder_kl.py`` ``AutoencoderKL.decode``; ``models/autoencoders/vae.py`` ``Decoder``;
+``models/resnet.py`` ``ResnetBlock2D``; ``models/attention_processor.py`` ``Attention``; ``models/upsampling.py``
+``Upsample2D``; as of diffusers 0.2x) with the sd-vae-ft-mse ``config.json`` values, and parity of the native decoder
+is anchored on this restatement only (say "unpinned" wherever it is quoted):
+
+    latent_channels 4, out_channels 3, block_out_channels (128, 256, 512, 512), layers_per_block 2,
+    norm_num_groups 32 (GroupNorm eps 1e-6), act_fn silu, mid-block attention with ONE head of 512 channels
+
+    decode(z):  z = post_quant_conv(z)                     1x1, 4 -> 4
+                h = conv_in(z)                              3x3, 4 -> 512
+                h = mid.resnets[0](h); h = mid.attentions[0](h); h = mid.resnets[1](h)
+                for i, ch in enumerate((512, 512, 256, 128)):            # reversed block_out_channels
+                    3 x ResnetBlock2D(-> ch)  (first one changes the width: 1x1 conv_shortcut)
+                    if i < 3: nearest x2 then conv3x3(ch -> ch)
+                h = conv_out(silu(conv_norm_out(h)))        GroupNorm(32, 128) -> SiLU -> 3x3, 128 -> 3
+    ResnetBlock2D(x):  h = conv1(silu(norm1(x))); h = conv2(silu(norm2(h))); return (shortcut(x) + h) / 1.0
+    Attention(x):      r = x; x = group_norm(x).view(B, C, HW).T; q, k, v = to_q(x), to_k(x), to_v(x)
+                       x = softmax(q k^T / sqrt(C)) v; x = to_out[0](x); return x.T.view(B, C, H, W) + r
+
+State-dict keys = the ``decoder.*`` and ``post_quant_conv.*`` entries of the diffusers checkpoint (new attention names
+``to_q / to_k / to_v / to_out.0``; the original sd-vae-ft-mse file uses ``query / key / value / proj_attn``, which
+diffusers renames at load time - :func:`rename_legacy_keys`).
+
+Also the post-processing of the generation loop (test_flow_latent_ddp.py:131-135):
+``(clamp((x + 1) / 2, 0, 1) * 255).permute(0, 2, 3, 1).to(uint8)`` -> :func:`to_uint8_nhwc` (float -> uint8 truncates).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclass(frozen=True)
+class VAEConfig:
+    latent_channels: int = 4
+    out_channels: int = 3
+    block_out_channels: tuple = (128, 256, 512, 512)
+    layers_per_block: int = 2
+    norm_num_groups: int = 32
+    eps: float = 1e-6
+
+
+def decoder_plan(cfg: VAEConfig):
+    """[(prefix, kind, cin, cout)] in execution order; kind in {res, attn, up}."""
+    rev = tuple(reversed(cfg.block_out_channels))
+    ch = rev[0]
+    plan = [("decoder.mid_block.resnets.0", "res", ch, ch), ("decoder.mid_block.attentions.0", "attn", ch, ch),
+            ("decoder.mid_block.resnets.1", "res", ch, ch)]
+    for i, out in enumerate(rev):
+        for j in range(cfg.layers_per_block + 1):
+            plan.append((f"decoder.up_blocks.{i}.resnets.{j}", "res", ch, out))
+            ch = out
+        if i != len(rev) - 1:
+            plan.append((f"decoder.up_blocks.{i}.upsamplers.0", "up", ch, ch))
+    return plan, rev[0], ch
+
+
+def param_shapes(cfg: VAEConfig = VAEConfig()):
+    """Ordered {key: shape} of the decoder-side state dict (diffusers registration order within each module)."""
+    plan, c0, c_last = decoder_plan(cfg)
+    L = cfg.latent_channels
+    sh = {"decoder.conv_in.weight": (c0, L, 3, 3), "decoder.conv_in.bias": (c0,)}
+
+    def res(p, cin, cout):
+        sh[p + ".norm1.weight"] = (cin,)
+        sh[p + ".norm1.bias"] = (cin,)
+        sh[p + ".conv1.weight"] = (cout, cin, 3, 3)
+        sh[p + ".conv1.bias"] = (cout,)
+        sh[p + ".norm2.weight"] = (cout,)
+        sh[p + ".norm2.bias"] = (cout,)
+        sh[p + ".conv2.weight"] = (cout, cout, 3, 3)
+        sh[p + ".conv2.bias"] = (cout,)
+        if cin != cout:
+            sh[p + ".conv_shortcut.weight"] = (cout, cin, 1, 1)
+            sh[p + ".conv_shortcut.bias"] = (cout,)
+
+    def attn(p, c):
+        sh[p + ".group_norm.weight"] = (c,)
+        sh[p + ".group_norm.bias"] = (c,)
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            sh[f"{p}.{n}.weight"] = (c, c)
+            sh[f"{p}.{n}.bias"] = (c,)
+
+    # diffusers registers up_blocks before mid_block in Decoder.__init__; the ORDER of a state dict does not matter
+    # for load_state_dict - execution order is used here for readability.
+    for p, kind, cin, cout in plan:
+        if kind == "res":
+            res(p, cin, cout)
+        elif kind == "attn":
+            attn(p, cin)
+        else:
+            sh[p + ".conv.weight"] = (cout, cin, 3, 3)
+            sh[p + ".conv.bias"] = (cout,)
+    sh["decoder.conv_norm_out.weight"] = (c_last,)
+    sh["decoder.conv_norm_out.bias"] = (c_last,)
+    sh["decoder.conv_out.weight"] = (cfg.out_channels, c_last, 3, 3)
+    sh["decoder.conv_out.bias"] = (cfg.out_channels,)
+    sh["post_quant_conv.weight"] = (L, L, 1, 1)
+    sh["post_quant_conv.bias"] = (L,)
+    return sh
+
+
+def synthetic_state_dict(cfg: VAEConfig = VAEConfig(), seed: int = 1):
+    """Seeded non-degenerate decoder weights (the real ones are a network download): conv / linear U(-a, a) with
+    a = 1/sqrt(fan_in), GroupNorm weight 1 + 0.1 N, bias 0.1 N, biases 0.02 N; one generator per tensor, seeded from
+    (seed, crc32(key)) => independent of the key order."""
+    import zlib
+    sd = {}
+    for k, shp in param_shapes(cfg).items():
+        g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(k.encode()))
+        leaf = k.rsplit(".", 2)[-2]
+        if "norm" in leaf:
+            sd[k] = (1.0 + 0.1 * torch.randn(shp, generator=g)) if k.endswith("weight") else 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith(".bias"):
+            sd[k] = 0.02 * torch.randn(shp, generator=g)
+        else:
+            fan_in = int(math.prod(shp[1:]))
+            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
+    return sd
+
+
+LEGACY_ATTN = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}
+
+
+def rename_legacy_keys(sd):
+    """diffusers ``_convert_deprecated_attention_blocks``: query/key/value/proj_attn -> to_q/to_k/to_v/to_out.0."""
+    out = {}
+    for k, v in sd.items():
+        parts = k.split(".")
+        if len(parts) >= 2 and parts[-2] in LEGACY_ATTN and "attentions" in parts:
+            parts[-2] = LEGACY_ATTN[parts[-2]]
+            k = ".".join(parts)
+        out[k] = v
+    return out
+
+
+def _gn(x, sd, p, cfg):
+    return F.group_norm(x, cfg.norm_num_groups, sd[p + ".weight"], sd[p + ".bias"], eps=cfg.eps)
+
+
+def resnet_block(sd, p, x, cfg):
+    h = F.conv2d(F.silu(_gn(x, sd, p + ".norm1", cfg)), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
+    h = F.conv2d(F.silu(_gn(h, sd, p + ".norm2", cfg)), sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
+    if p + ".conv_shortcut.weight" in sd:
+        x = F.conv2d(x, sd[p + ".conv_shortcut.weight"], sd[p + ".conv_shortcut.bias"])
+    return x + h
+
+
+def attention_block(sd, p, x, cfg):
+    B, C, H, W = x.shape
+    h = _gn(x, sd, p + ".group_norm", cfg).reshape(B, C, H * W).transpose(1, 2)
+    q = F.linear(h, sd[p + ".to_q.weight"], sd[p + ".to_q.bias"])
+    k = F.linear(h, sd[p + ".to_k.weight"], sd[p + ".to_k.bias"])
+    v = F.linear(h, sd[p + ".to_v.weight"], sd[p + ".to_v.bias"])
+    a = torch.softmax(q @ k.transpose(1, 2) * (1.0 / math.sqrt(C)), dim=-1) @ v       # one head of C channels
+    a = F.linear(a, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
+    return a.transpose(1, 2).reshape(B, C, H, W) + x
+
+
+@torch.no_grad()
+def vae_decode(sd, z, cfg: VAEConfig = VAEConfig(), return_features: bool = False):
+    """``AutoencoderKL.decode(z).sample``: z [B, 4, h, w] fp32 -> [B, 3, 8h, 8w] fp32."""
+    plan, _, _ = decoder_plan(cfg)
+    h = F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    h = F.conv2d(h, sd["decoder.conv_in.weight"], sd["decoder.conv_in.bias"], padding=1)
+    feats = []
+    for p, kind, cin, cout in plan:
+        if kind == "res":
+            h = resnet_block(sd, p, h, cfg)
+        elif kind == "attn":
+            h = attention_block(sd, p, h, cfg)
+        else:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+            h = F.conv2d(h, sd[p + ".conv.weight"], sd[p + ".conv.bias"], padding=1)
+        if return_features:
+            feats.append((p, h))
+    h = F.silu(_gn(h, sd, "decoder.conv_norm_out", cfg))
+    out = F.conv2d(h, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
+    return (out, feats) if return_features else out
+
+
+def to_uint8_nhwc(img: torch.Tensor) -> torch.Tensor:
+    """test_flow_latent_ddp.py:131-135 (``to_range_0_1`` = (x + 1) / 2): [B, 3, H, W] fp32 -> [B, H, W, 3] uint8."""
+    return (torch.clamp((img + 1.0) / 2.0, 0, 1) * 255.0).permute(0, 2, 3, 1).to(torch.uint8)
+
+
+def decode_flops_per_image(cfg: VAEConfig = VAEConfig(), latent_side: int = 32) -> float:
+    """Algorithmic FLOPs (2 x MAC) of one decode: convolutions + the mid attention (GEMM terms only)."""
+    plan, c0, c_last = decoder_plan(cfg)
+    side = latent_side
+    fl = 2.0 * side * side * (cfg.latent_channels ** 2 + 9 * cfg.latent_channels * c0)
+    for p, kind, cin, cout in plan:
+        px = side * side
+        if kind == "res":
+            fl += 2.0 * px * 9 * (cin * cout + cout * cout) + (2.0 * px * cin * cout if cin != cout else 0.0)
+        elif kind == "attn":
+            fl += 2.0 * px * 4 * cin * cin + 4.0 * px * px * cin
+        else:
+            side *= 2
+            fl += 2.0 * side * side * 9 * cin * cout
+    fl += 2.0 * side * side * 9 * c_last * cfg.out_channels
+    return fl

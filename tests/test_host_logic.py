@@ -207,3 +207,60 @@ def test_sampler_label_validation():
         lfm_b200.UNetModel(image_size=32, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=1,
                            attention_resolutions=(2,), channel_mult=(1, 2), num_heads=2, num_heads_upsample=4,
                            use_scale_shift_norm=True)
+
+
+def test_vae_decoder_state_dict_surface():
+    """lfm_b200.AutoencoderKL holds the decoder-side keys of the diffusers checkpoint (oracle.vae.param_shapes restates
+    them), accepts a full / legacy-named checkpoint, and refuses to run on the CPU."""
+    from oracle import vae as ovae
+    vae = lfm_b200.AutoencoderKL()
+    want = ovae.param_shapes(ovae.VAEConfig())
+    got = {k: tuple(v.shape) for k, v in vae.state_dict().items()}
+    assert got == want and len(got) == 140
+    sd = lfm_b200.synthetic_vae_state_dict(vae, 3)
+    ref = ovae.synthetic_state_dict(ovae.VAEConfig(), 3)
+    assert all(torch.equal(sd[k], ref[k]) for k in ref)
+    # a full checkpoint with the legacy attention names (what stabilityai/sd-vae-ft-mse ships) loads strictly
+    legacy = {}
+    for k, v in sd.items():
+        for new, old in (("to_q", "query"), ("to_k", "key"), ("to_v", "value"), ("to_out.0", "proj_attn")):
+            if f".attentions.0.{new}." in k:
+                k = k.replace(f".{new}.", f".{old}.")
+        legacy[k] = v
+    legacy["encoder.conv_in.weight"] = torch.zeros(128, 3, 3, 3)
+    legacy["quant_conv.weight"] = torch.zeros(8, 8, 1, 1)
+    vae.load_state_dict(legacy, strict=True)
+    assert torch.equal(vae.decoder.mid_block.attentions[0].to_out[0].weight, sd["decoder.mid_block.attentions.0.to_out.0.weight"])
+    with pytest.raises(RuntimeError):
+        bad = dict(sd)
+        bad.pop("decoder.conv_out.bias")
+        vae.load_state_dict(bad, strict=True)
+    with pytest.raises(RuntimeError):                              # no CPU path
+        vae.decode(torch.randn(1, 4, 32, 32))
+    with pytest.raises(FileNotFoundError):                         # no hub access: only local directories
+        lfm_b200.AutoencoderKL.from_pretrained("stabilityai/sd-vae-ft-mse")
+    # post-processing restatement: truncation, not rounding (test_flow_latent_ddp.py:131-135)
+    x = torch.tensor([[[[-1.5, -1.0, 0.0]], [[0.999, 1.0, 2.0]], [[0.2, 0.4, 0.6]]]])
+    u = ovae.to_uint8_nhwc(x)
+    assert u.shape == (1, 1, 3, 3) and u[0, 0, :, 0].tolist() == [0, 0, 127] and u[0, 0, :, 1].tolist() == [254, 255, 255]
+
+
+def test_image_sink_writes_files_in_order(tmp_path):
+    """The generation loop's file sink (lfm_b200.cli.ImageSink): batches handed over without blocking are all on disk
+    after close(), each file holding its own image (decoded back and compared), buffers recycled across batches."""
+    import numpy as np
+    from PIL import Image
+    from lfm_b200.cli import ImageSink
+    sink = ImageSink(torch.device("cpu"), threads=3)
+    want = {}
+    g = torch.Generator().manual_seed(0)
+    for b in range(5):
+        u8 = (torch.rand(4, 1, 1, 3, generator=g) * 255).to(torch.uint8).expand(4, 16, 16, 3).contiguous()   # flat colours survive JPEG
+        paths = [str(tmp_path / f"{b * 4 + j}.png") for j in range(4)]
+        sink.put(u8, paths)
+        for j, p in enumerate(paths):
+            want[p] = u8[j].numpy().copy()
+    sink.close()
+    assert len(list(tmp_path.iterdir())) == 20
+    for p, arr in want.items():
+        assert np.array_equal(np.asarray(Image.open(p)), arr)
