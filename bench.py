@@ -479,6 +479,19 @@ def main():
         per = max(1, 128 // world)
         other["cfg5_strong"] = {"what": f"DiT-L/2 Euler NFE sweep, GLOBAL batch 128 => {per} per GPU (M = {per * 256} token rows), dp{world}",
                                 "rows": sweep(per, (10, 20, 50, 100)) if world > 1 else "identical to cfg5_weak at 1 GPU"}
+        if world == 1:
+            # the per-GPU shares of the strong-scaling run (global 128 on 2 / 4 / 8 GPUs) measured on ONE GPU: what
+            # strong scaling can reach is tflops(share) / tflops(128)
+            rows = []
+            for share, n_gpus in ((64, 2), (32, 4), (16, 8)):
+                r = sweep(share, (50,))[0]
+                r.update({"batch_per_gpu": share, "stands_for_n_gpus": n_gpus})
+                rows.append(r)
+            base = [r for r in other["cfg5_weak"]["rows"] if r["euler_nfe"] == 50][0]["tflops_per_gpu"]
+            for r in rows:
+                r["predicted_strong_scaling_efficiency"] = round(r["tflops_per_gpu"] / base, 3)
+            other["cfg5_strong_shares_on_one_gpu"] = {"what": "Euler-50 at the per-GPU batch of a global-128 run on 2 / 4 / 8 GPUs, one GPU",
+                                                      "rows": rows}
     del net
     torch.cuda.empty_cache()
     if not args.no_extras:

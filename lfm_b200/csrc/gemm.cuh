@@ -40,6 +40,16 @@ struct GemmEpi {
     int reverse_m = 0;
     // Pair kernel, EPI_GATE_RESID_F32: the TMA reduce-add into the residual stream carries the evict_last L2 policy.
     int l2_keep = 0;
+    // Pair kernel with the LayerNorm finisher (gemm2_bf16_tcgen05<EPI_GATE_RESID_F32, true>; N == ldo == D): once every
+    // column tile of a 256-row block of the residual stream has been added, the CTA that added the last one also
+    // produces the NEXT layer's operand  ln_out = LayerNorm(x) * (1 + ln_scale) + ln_shift  (bf16; models/DiT.py:20-21,
+    // 129-130) for those rows while they are still in L2 - the stand-alone LayerNorm pass over x disappears.
+    // rb_count[m_blk] counts arrivals (zero on entry; reset by the finisher).
+    int* rb_count = nullptr;
+    __nv_bfloat16* ln_out = nullptr;
+    const float* ln_shift = nullptr;  // [sample * ln_stride + column]
+    const float* ln_scale = nullptr;
+    int ln_stride = 0;
 };
 constexpr double kGnFixScale = 268435456.0;  // 2^28
 

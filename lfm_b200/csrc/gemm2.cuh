@@ -20,6 +20,7 @@
 namespace lfm {
 
 constexpr int kG2Threads = 384;
+constexpr int kG2ThreadsFin = 512;  // + 4 LayerNorm finisher warps (warps 12..15)
 constexpr int kG2BlockN = 256;
 constexpr int kG2Stages = 6;
 constexpr int kG2ABytes = 128 * 64 * 2;
@@ -221,8 +222,63 @@ LFM_DEVICE void stage_row_bf16_half(uint8_t* stg, int lane, const float* f, int 
     }
 }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
+// LayerNorm + adaLN modulate of `nrows` rows of the fp32 residual stream (just completed by the reduce-adds of this
+// launch, so read through L2: ld.global.cg), executed by the 4 finisher warps of one CTA: 2 rows per warp in flight.
+// Same arithmetic as ln_modulate_kernel (two-pass statistics in registers, eps 1e-6).
+LFM_DEVICE void ln_finish_rows(const GemmEpi& ep, int row0, int nrows, int M, int D, int wf, int lane) {
+    constexpr int MAXV = 9;  // D <= 1152
+    const int nv = D / 128;
+    const float* x = static_cast<const float*>(ep.out);
+    const float inv_d = 1.0f / static_cast<float>(D);
+    for (int r = row0 + 2 * wf; r < row0 + nrows; r += 8) {
+        float4 v[2][MAXV];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int row = r + u;
+            ok[u] = row < M && row < row0 + nrows;
+            const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(ok[u] ? row : row0) * D);
+#pragma unroll
+            for (int m = 0; m < MAXV; ++m)
+                if (m < nv) v[u][m] = __ldcg(xp + m * 32 + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;  // warp-uniform
+            const int row = r + u;
+            float s = 0.f;
+#pragma unroll
+            for (int m = 0; m < MAXV; ++m)
+                if (m < nv) s += (v[u][m].x + v[u][m].y) + (v[u][m].z + v[u][m].w);
+            const float mean = warp_sum(s) * inv_d;
+            float ss = 0.f;
+#pragma unroll
+            for (int m = 0; m < MAXV; ++m)
+                if (m < nv) {
+                    const float a = v[u][m].x - mean, b = v[u][m].y - mean, c = v[u][m].z - mean, d = v[u][m].w - mean;
+                    ss += (a * a + b * b) + (c * c + d * d);
+                }
+            const float rstd = rsqrtf(warp_sum(ss) * inv_d + 1e-6f);
+            const size_t boff = static_cast<size_t>(row / ep.rows_per_sample) * ep.ln_stride;
+            const float4* shp = reinterpret_cast<const float4*>(ep.ln_shift + boff);
+            const float4* scp = reinterpret_cast<const float4*>(ep.ln_scale + boff);
+            uint2* yp = reinterpret_cast<uint2*>(ep.ln_out + static_cast<size_t>(row) * D);
+#pragma unroll
+            for (int m = 0; m < MAXV; ++m)
+                if (m < nv) {
+                    const float4 sh = __ldg(shp + m * 32 + lane), sc = __ldg(scp + m * 32 + lane);
+                    const float a = fmaf((v[u][m].x - mean) * rstd, 1.f + sc.x, sh.x);
+                    const float b = fmaf((v[u][m].y - mean) * rstd, 1.f + sc.y, sh.y);
+                    const float c = fmaf((v[u][m].z - mean) * rstd, 1.f + sc.z, sh.z);
+                    const float d = fmaf((v[u][m].w - mean) * rstd, 1.f + sc.w, sh.w);
+                    yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+                }
+        }
+    }
+}
+
+template <int EPI, bool FIN = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FIN ? kG2ThreadsFin : kG2Threads, 1)
 gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], box {64, 128}
                    const __grid_constant__ CUtensorMap tmap_b,   // W [N, K], box {64, 128}
                    const __grid_constant__ CUtensorMap tmap_out, // out [M, ldo]: box {128 bytes, 32 rows}, 128B swizzle
@@ -239,6 +295,14 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
     uint64_t* tmem_empty = bars + 2 * kG2Stages + 2;  // [2] leader only: 16 epilogue warps (8 per CTA) arrive
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kG2Stages + 4);
     uint8_t* smem_stage = smem + kG2Stages * kG2StageBytes + 1024;  // 8 x 4 KB epilogue staging tiles (1024-aligned)
+    // LayerNorm finisher hand-off (FIN): completed row blocks queued by this CTA's epilogue warps for its finisher warps
+    __shared__ int fin_queue[16];  // -1 = empty
+    __shared__ int fin_pushed, fin_exit;
+    if (FIN && threadIdx.x < 16) fin_queue[threadIdx.x] = -1;
+    if (FIN && threadIdx.x == 0) {
+        fin_pushed = 0;
+        fin_exit = 0;
+    }
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -391,7 +455,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
         // ===================== epilogue: 8 warps, 128 rows x (2 x 128 columns) =====================
         // TMEM -> registers -> (bias / GELU / gate) -> swizzled smem staging tile -> TMA store, or TMA reduce-add
         // for the gated residual (x += g * (acc + b) is applied at L2: the SM never reads x).
@@ -481,8 +545,48 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 acc = 0;
                 acc_phase ^= 1;
             }
+            if (FIN && EPI == EPI_GATE_RESID_F32 && lane == 0) {
+                // this warp's share of the tile is in the residual stream once its reduce-adds have been performed
+                tma_store_wait<0>();
+                fence_proxy_async();
+                __threadfence();                                             // release
+                const int units = width == kG2BlockN ? 2 : 1;               // a half-width tail tile counts half
+                const int old = atomicAdd(ep.rb_count + m_blk, units);
+                if (old + units == 32 * n_blocks) {                          // 16 warps x 2 units x column tiles: block complete
+                    atomicExch(ep.rb_count + m_blk, 0);                      // ready for the next launch
+                    __threadfence();                                         // acquire
+                    const int slot = atomicAdd(&fin_pushed, 1);              // reserve a queue slot, then publish the block index
+                    atomicExch(&fin_queue[slot & 15], m_blk);
+                }
+            }
         }
         if (lane == 0) tma_store_wait<0>();  // all global writes of this warp are complete before the CTA exits
+        if (FIN && lane == 0) {
+            __threadfence_block();
+            atomicAdd(&fin_exit, 1);
+        }
+    } else if (FIN && warp >= 12) {
+        // ===================== LayerNorm finisher: 4 warps, woken by this CTA's epilogue warps =====================
+        const int wf = warp - 12;
+        volatile int* vp = &fin_pushed;
+        volatile int* ve = &fin_exit;
+        volatile int* vq = fin_queue;
+        int done = 0;
+        for (;;) {
+            if (*vp <= done) {
+                if (*ve == 8 && *vp <= done) break;  // all epilogue warps of this CTA have left their loops: no more pushes
+                __nanosleep(256);
+                continue;
+            }
+            int mb;
+            while ((mb = vq[done & 15]) < 0) __nanosleep(32);  // the slot is reserved; its value arrives a moment later
+            __syncwarp();
+            asm volatile("bar.sync 2, 128;" ::: "memory");     // all 4 finisher warps have read the slot
+            if (warp == 12 && lane == 0) vq[done & 15] = -1;
+            ++done;
+            __threadfence();                                    // acquire: the rows of block mb are complete and visible
+            ln_finish_rows(ep, mb * 256, 256, M, N, wf, lane);
+        }
     }
 
     tc_fence_before();

@@ -449,13 +449,40 @@ __global__ void rk_combine_kernel(const float* __restrict__ y0, RkPtrs kp, int n
     y_out[i] = y0[i] + acc;
 }
 
+// One attempted dopri5 step's numbers, uploaded once per step (the captured step graph reads them from device memory):
+// stage i forms y0 + sum_j coef[i][j] k_j (coefficients already multiplied by dt) and evaluates the network at t[i].
+struct DpStep {
+    float coef[6][8];
+    float t[8];      // model time of the 6 stage evaluations (t = -s)
+    float cerr[8];   // dt * c_err
+};
+__global__ void rk_combine_dev_kernel(const float* __restrict__ y0, RkPtrs kp, int nk, const float* __restrict__ coef,
+                                      float* __restrict__ y_out, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int j = 0; j < nk; ++j) acc = fmaf(kp.k[j][i], coef[j], acc);
+    y_out[i] = y0[i] + acc;
+}
+// accepted step: y0 <- y1, f0 <- k7 (FSAL) as copies, so that the captured graph keeps its buffer pointers
+__global__ void dp_accept_kernel(float* __restrict__ y0, const float* __restrict__ y1, float* __restrict__ k0,
+                                 const float* __restrict__ k6, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    y0[i] = y1[i];
+    k0[i] = k6[i];
+}
+
 // partial[blk] = sum over this block's elements of ((a - b) / (atol + rtol * max(|y0|, |y1|)))^2
 // a == nullptr: a = sum_j coef[j] * k[j] (the embedded error estimate).  b may be nullptr.  Warp-shuffle reduce.
 constexpr int kRmsBlocks = 128;
 __global__ void __launch_bounds__(256)
 rms_ratio_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, RkPtrs kp,
                          RkCoef coef, const float* __restrict__ y0, const float* __restrict__ y1,
-                         float atol, float rtol, size_t n, double* __restrict__ partial) {
+                         float atol, float rtol, size_t n, double* __restrict__ partial,
+                         const float* __restrict__ coef_dev = nullptr /* overrides coef (captured step graph) */) {
+    if (coef_dev != nullptr)
+        for (int j = 0; j < 7; ++j) coef.c[j] = coef_dev[j];
     __shared__ double wsum[8];
     double acc = 0.0;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;

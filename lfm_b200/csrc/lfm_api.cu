@@ -174,6 +174,21 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
                     (tbh != nullptr && split_env) ? 1 : 0, ksplit, split_row_pitch);
 }
 
+// Pair kernel with the LayerNorm finisher (ep.ln_out != nullptr; N == D): see GemmEpi::rb_count
+static cudaError_t launch_gemm2_fin(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, int M,
+                                    int N, int K, const GemmEpi& ep, const CUtensorMap* tbh) {
+    static DevOnce once;
+    auto kern = gemm2_bf16_tcgen05<EPI_GATE_RESID_F32, true>;
+    if (cudaError_t e = smem_opt_in(once, kern, kG2SmemBytes)) return e;
+    const int tiles = ((M + 255) / 256) * ((N + kG2BlockN - 1) / kG2BlockN);
+    int clusters = g_num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    static const int split_env = env_int("LFM_GEMM_SPLIT", 1);
+    const ConvGeom cg{0, 0, 0, 0, 1};
+    return launch_k(kern, dim3(2 * clusters), kG2ThreadsFin, kG2SmemBytes, s, ta, tb, tout, tbh != nullptr ? *tbh : tb, M, N, K, ep, cg,
+                    (tbh != nullptr && split_env) ? 1 : 0, 1, 0);
+}
+
 // 4-CTA cluster kernel (two pairs sharing A by multicast; 256 x 512 block per cluster)
 template <int EPI>
 static cudaError_t launch_gemm4_inst(cudaStream_t s, const CUtensorMap& ta64, const CUtensorMap& tb, const CUtensorMap& tout,
@@ -233,6 +248,7 @@ static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUte
         const ConvGeom cg{0, 0, 0, 0, 1};
         if (epi == EPI_BIAS_BF16) return launch_gemm2_inst<EPI_BIAS_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
         if (epi == EPI_BIAS_GELU_BF16) return launch_gemm2_inst<EPI_BIAS_GELU_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
+        if (epi == EPI_GATE_RESID_F32 && ep.ln_out != nullptr) return launch_gemm2_fin(s, ta, tb, *tout, M, N, K, ep, tbh);
         if (epi == EPI_GATE_RESID_F32) return launch_gemm2_inst<EPI_GATE_RESID_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
         if (epi == EPI_BIAS_F32) return launch_gemm2_inst<EPI_BIAS_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
         return cudaErrorInvalidValue;
@@ -346,6 +362,8 @@ struct lfm_ctx {
     int attn_variant = 0;  // 0 = P in TMEM, 1 = P via smem
     int zigzag = 0;        // LFM_ZIGZAG: alternate the row-sweep direction of consecutive kernels (L2 reuse)
     int l2_hint = 0;       // LFM_L2_HINT: evict_last L2 policy on the residual stream's TMA traffic (measured: no gain)
+    int ln_fuse = 1;       // LFM_LN_FUSE: LayerNorm + modulate of the next layer produced by the residual GEMM's finisher warps
+    int* rb_count = nullptr;  // per 256-row block arrival counters of the finisher (GemmEpi::rb_count)
     int bn_qkv = 256, bn_proj = 256, bn_fc1 = 256, bn_fc2 = 256, bn_mod = 256;
 
     std::unordered_map<std::string, ParamSlot> params;
@@ -377,6 +395,8 @@ struct lfm_ctx {
     long long* y_buf = nullptr;
     StepState* step_state = nullptr;
     float* ratio_host = nullptr;  // pinned
+    DpStep* dp_dev = nullptr;     // dopri5: parameters of the step being attempted (device copy read by the step graph)
+    DpStep* dp_host = nullptr;    // pinned
     struct StepGraph {
         cudaGraphExec_t exec = nullptr;
         int launches = 0;  // kernels per replay (measured on the warm-up run)
@@ -467,6 +487,7 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     ctx->attn_variant = env_int("LFM_ATTN_VARIANT", 3);
     ctx->zigzag = env_int("LFM_ZIGZAG", 1);
     ctx->l2_hint = env_int("LFM_L2_HINT", 0);
+    ctx->ln_fuse = env_int("LFM_LN_FUSE", 1);
     const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
 
     if (dev_alloc(ctx, &ctx->pos, (size_t)T * D)) return 1;
@@ -601,6 +622,8 @@ static int alloc_solver_state(lfm_ctx* ctx, int R) {
     if (dev_alloc(ctx, &ctx->y_buf, (size_t)R)) return 1;
     if (dev_alloc(ctx, &ctx->step_state, 1)) return 1;
     CUDA_OK(cudaMallocHost(&ctx->ratio_host, 64));
+    if (dev_alloc(ctx, &ctx->dp_dev, 1)) return 1;
+    CUDA_OK(cudaMallocHost(&ctx->dp_host, sizeof(DpStep)));
     return 0;
 }
 
@@ -635,6 +658,7 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
     if (dev_alloc(ctx, &ctx->tfreq, (size_t)R * 256)) return 1;
     if (dev_alloc(ctx, &ctx->h1, (size_t)R * D)) return 1;
     if (dev_alloc(ctx, &ctx->v_net, (size_t)R * ctx->chw)) return 1;
+    if (dev_alloc(ctx, &ctx->rb_count, (M + 255) / 256 + 1)) return 1;
     if (alloc_solver_state(ctx, R)) return 1;
 
     // default: the CTA-pair kernel for every token-level GEMM (LFM_BN_* = 128 / 256 selects the 1-CTA kernel)
@@ -729,10 +753,13 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         dir ^= 1;
         return d;
     };
+    // LayerNorm fusion: the proj / fc2 GEMMs (pair kernel, full rows: N == D) also emit the LayerNorm-modulated operand of
+    // the layer that follows them; only the very first LayerNorm of the network is a stand-alone pass.
+    const bool fuse = ctx->ln_fuse && ctx->bn_proj == kGemmPair && ctx->bn_fc2 == kGemmPair;
     for (int l = 0; l < L; ++l) {
         BlockW& b = ctx->blk[l];
         const float* mb = ctx->mod + (size_t)l * 6 * D;  // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
-        {
+        if (l == 0 || !fuse) {
             const int d = next_dir();
             CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb, mb + D, Nmod, T, M, D, (zig ? 1 + d : 0) | (ctx->l2_hint ? 4 : 0)));
             ctx->launches++;
@@ -757,10 +784,17 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
             GemmEpi ep{b.b_proj, ctx->x_tok, D, mb + 2 * D, Nmod, T};
             ep.reverse_m = next_dir();
             ep.l2_keep = ctx->l2_hint;
+            if (fuse) {  // x += gate_msa * proj(...), then xn = LN(x) * (1 + scale_mlp) + shift_mlp   (models/DiT.py:129-130)
+                ep.rb_count = ctx->rb_count;
+                ep.ln_out = ctx->xn;
+                ep.ln_shift = mb + 3 * D;
+                ep.ln_scale = mb + 4 * D;
+                ep.ln_stride = Nmod;
+            }
             CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok, &b.tmh_proj, &ctx->tm64_attn));
             ctx->launches++;
         }
-        {
+        if (!fuse) {
             const int d = next_dir();
             CUDA_OK(launch_ln(s, ctx->x_tok, ctx->xn, mb + 3 * D, mb + 4 * D, Nmod, T, M, D, (zig ? 1 + d : 0) | (ctx->l2_hint ? 4 : 0)));
             ctx->launches++;
@@ -775,6 +809,14 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
             GemmEpi ep{b.b_fc2, ctx->x_tok, D, mb + 5 * D, Nmod, T};
             ep.reverse_m = next_dir();
             ep.l2_keep = ctx->l2_hint;
+            if (fuse && l + 1 < L) {  // x += gate_mlp * fc2(...), then the NEXT block's xn = LN(x) * (1 + scale_msa) + shift_msa
+                const float* mn = ctx->mod + (size_t)(l + 1) * 6 * D;
+                ep.rb_count = ctx->rb_count;
+                ep.ln_out = ctx->xn;
+                ep.ln_shift = mn;
+                ep.ln_scale = mn + D;
+                ep.ln_stride = Nmod;
+            }
             CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep, &ctx->tmo_xtok, &b.tmh_fc2, &ctx->tm64_hmid));
             ctx->launches++;
         }
@@ -1094,18 +1136,88 @@ static int dp_func(Dopri& d, float s_time, const float* yv, float* k_out) {
     return 0;
 }
 
-static int dp_rms(Dopri& d, const float* a, const float* b, const RkCoef& coef, const float* y0, const float* y1,
-                  float atol, float rtol, float* out_host) {
+// rms(a - b) relative to atol + rtol * |y0| into ctx->ratio[slot] (no synchronisation)
+static int dp_rms_launch(Dopri& d, const float* a, const float* b, const float* y0, float atol, float rtol, int slot) {
     lfm_ctx* ctx = d.ctx;
     RkPtrs kp;
     for (int j = 0; j < 7; ++j) kp.k[j] = ctx->kbuf[j];
-    rms_ratio_partial_kernel<<<kRmsBlocks, 256, 0, d.s>>>(a, b, kp, coef, y0, y1, atol, rtol, d.n, ctx->partial);
+    rms_ratio_partial_kernel<<<kRmsBlocks, 256, 0, d.s>>>(a, b, kp, RkCoef{}, y0, y0, atol, rtol, d.n, ctx->partial, nullptr);
     LAUNCH_OK();
-    rms_finalize_kernel<<<1, 32, 0, d.s>>>(ctx->partial, kRmsBlocks, d.n, ctx->ratio);
+    rms_finalize_kernel<<<1, 32, 0, d.s>>>(ctx->partial, kRmsBlocks, d.n, ctx->ratio + slot);
     LAUNCH_OK();
-    CUDA_OK(cudaMemcpyAsync(ctx->ratio_host, ctx->ratio, sizeof(float), cudaMemcpyDeviceToHost, d.s));
+    return 0;
+}
+static int dp_fetch(Dopri& d, int count) {  // ctx->ratio[0..count) -> ctx->ratio_host, one synchronisation
+    lfm_ctx* ctx = d.ctx;
+    CUDA_OK(cudaMemcpyAsync(ctx->ratio_host, ctx->ratio, count * sizeof(float), cudaMemcpyDeviceToHost, d.s));
     CUDA_OK(cudaStreamSynchronize(d.s));
-    *out_host = ctx->ratio_host[0];
+    return 0;
+}
+
+// One attempted Dormand-Prince step, recorded into ctx->stream (live or under capture).  Every number that changes from
+// step to step (the stage coefficients dt * beta_ij, the six stage times, dt * c_err) is read from ctx->dp_dev, and the
+// buffers are fixed (an accepted step COPIES y1 -> y0 and k7 -> k1 instead of swapping pointers), so one captured
+// graph serves the whole integration: per attempted step the host uploads 300 bytes, launches one graph and reads
+// back one float.
+static int dp_record_step(Dopri& d, float atol, float rtol) {
+    lfm_ctx* ctx = d.ctx;
+    cudaStream_t s = d.s;
+    const size_t n = d.n;
+    RkPtrs kp;
+    for (int j = 0; j < 7; ++j) kp.k[j] = ctx->kbuf[j];
+    float* y0 = ctx->x_state;
+    float* y1 = ctx->x_pred;
+    float* ytmp = ctx->y_stage;
+    for (int i = 0; i < 6; ++i) {
+        float* yi = (i == 5) ? y1 : ytmp;
+        rk_combine_dev_kernel<<<blocks_for(n), 256, 0, s>>>(y0, kp, i + 1, ctx->dp_dev->coef[i], yi, n);
+        LAUNCH_OK();
+        if (eval_velocity(ctx, s, ctx->dp_dev->t + i, 1, yi, d.n_img, d.y, d.cfg_scale, ctx->kbuf[i + 1])) return 1;
+        negate_kernel<<<blocks_for(n), 256, 0, s>>>(ctx->kbuf[i + 1], n);
+        LAUNCH_OK();
+    }
+    rms_ratio_partial_kernel<<<kRmsBlocks, 256, 0, s>>>(nullptr, nullptr, kp, RkCoef{}, y0, y1, atol, rtol, n, ctx->partial,
+                                                        ctx->dp_dev->cerr);
+    LAUNCH_OK();
+    rms_finalize_kernel<<<1, 32, 0, s>>>(ctx->partial, kRmsBlocks, n, ctx->ratio);
+    LAUNCH_OK();
+    CUDA_OK(cudaMemcpyAsync(ctx->ratio_host, ctx->ratio, sizeof(float), cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
+static int dp_get_graph(Dopri& d, float atol, float rtol, cudaGraphExec_t* out, int* launches) {
+    lfm_ctx* ctx = d.ctx;
+    char key[160];
+    snprintf(key, sizeof(key), "dp_n%d_y%d_c%.6f_a%.9g_r%.9g", d.n_img, d.y != nullptr ? 1 : 0, d.cfg_scale > 1.0f ? d.cfg_scale : 0.f,
+             atol, rtol);
+    auto it = ctx->graphs.find(key);
+    if (it != ctx->graphs.end()) {
+        *out = it->second.exec;
+        *launches = it->second.launches;
+        return 0;
+    }
+    *out = nullptr;
+    *launches = 0;
+    if (env_int("LFM_NO_GRAPH", 0)) return 0;
+    // warm-up run outside of capture (lazily set function attributes); it only writes scratch: ytmp, y1, k2..k7, ratio
+    const int64_t before = ctx->launches;
+    if (dp_record_step(d, atol, rtol)) return 1;
+    CUDA_OK(cudaStreamSynchronize(d.s));
+    const int per = static_cast<int>(ctx->launches - before);
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(d.s, cudaStreamCaptureModeThreadLocal));
+    const int rc = dp_record_step(d, atol, rtol);
+    cudaError_t e = cudaStreamEndCapture(d.s, &graph);
+    ctx->launches = before;
+    if (rc) return 1;
+    if (e != cudaSuccess) return fail(ctx, "dopri5 graph capture failed: %s", cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+    CUDA_OK(cudaGraphDestroy(graph));
+    ctx->graphs[key].exec = exec;
+    ctx->graphs[key].launches = per;
+    *out = exec;
+    *launches = per;
     return 0;
 }
 
@@ -1131,26 +1243,33 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
     float* y1 = ctx->x_pred;
     float* ytmp = ctx->y_stage;
     float** k = ctx->kbuf;
-    CUDA_OK(cudaMemcpyAsync(y0, x_inout, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     const float atol_f = (float)atol, rtol_f = (float)rtol;
     RkPtrs kp;
     for (int j = 0; j < 7; ++j) kp.k[j] = k[j];
-    const RkCoef no_coef{};
 
+    // the step graph first: its warm-up run scribbles over the scratch buffers (never over y0 / k1, set below)
+    cudaGraphExec_t g_step = nullptr;
+    int l_step = 0;
+    CUDA_OK(cudaMemsetAsync(ctx->dp_dev, 0, sizeof(DpStep), s));
+    if (dp_get_graph(d, atol_f, rtol_f, &g_step, &l_step)) return 1;
+
+    CUDA_OK(cudaMemcpyAsync(y0, x_inout, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     double s0 = -t0;
     const double s_end = -t1;
-    // _before_integrate: f0 and the initial step (order 4 rule)
+    // _before_integrate: f0 and the initial step (order 4 rule); two synchronisations
     if (dp_func(d, (float)s0, y0, k[0])) return 1;
-    float d0, d1, d2;
-    if (dp_rms(d, y0, nullptr, no_coef, y0, y0, atol_f, rtol_f, &d0)) return 1;
-    if (dp_rms(d, k[0], nullptr, no_coef, y0, y0, atol_f, rtol_f, &d1)) return 1;
+    if (dp_rms_launch(d, y0, nullptr, y0, atol_f, rtol_f, 0)) return 1;
+    if (dp_rms_launch(d, k[0], nullptr, y0, atol_f, rtol_f, 1)) return 1;
+    if (dp_fetch(d, 2)) return 1;
+    const float d0 = ctx->ratio_host[0], d1 = ctx->ratio_host[1];
     float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
     h0 = fabsf(h0);
     axpy_kernel<<<blocks_for(n), 256, 0, s>>>(y0, k[0], h0, ytmp, n);
     LAUNCH_OK();
     if (dp_func(d, (float)(s0 + (double)h0), ytmp, k[1])) return 1;
-    if (dp_rms(d, k[1], k[0], no_coef, y0, y0, atol_f, rtol_f, &d2)) return 1;
-    d2 = fabsf(d2 / h0);
+    if (dp_rms_launch(d, k[1], k[0], y0, atol_f, rtol_f, 0)) return 1;
+    if (dp_fetch(d, 1)) return 1;
+    const float d2 = fabsf(ctx->ratio_host[0] / h0);
     float h1;
     if (d1 <= 1e-15f && d2 <= 1e-15f)
         h1 = fmaxf(1e-6f, h0 * 1e-3f);
@@ -1158,37 +1277,35 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
         h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / 5.0f);
     double dt = (double)fminf(100.f * h0, fabsf(h1));
 
-    double s_lo = s0, s_hi = s0;
-    float dt_last = 0.f;
+    double s_hi = s0;
     int64_t accepted = 0, rejected = 0;
     bool have_interp = false;
-    // y_prev (start of the last accepted step) is needed for the dense output: keep it in d_prime
-    float* y_prev = ctx->d_prime;
     while (s_end > s_hi) {
         if (accepted + rejected > 100000) return fail(ctx, "lfm_sample_dopri5: step limit exceeded");
         const double t0s = s_hi, t1s = t0s + dt;
         const float t0_32 = (float)t0s, dt_32 = (float)dt, t1_32 = (float)t1s;
+        DpStep* hp = ctx->dp_host;  // the previous step's upload has completed: every step ends with a synchronisation
+        memset(hp, 0, sizeof(DpStep));
         for (int i = 0; i < 6; ++i) {
-            RkCoef cb{};
-            for (int j = 0; j <= i; ++j) cb.c[j] = (float)DP_BETA[i][j] * dt_32;
-            float* yi = (i == 5) ? y1 : ytmp;
-            rk_combine_kernel<<<blocks_for(n), 256, 0, s>>>(y0, kp, i + 1, cb, yi, n);
-            LAUNCH_OK();
-            float ti;
-            if (DP_ALPHA[i] == 1.0)
-                ti = nextafterf(t1_32, t1_32 - 1.0f);
-            else
-                ti = t0_32 + (float)DP_ALPHA[i] * dt_32;
-            if (dp_func(d, ti, yi, k[i + 1])) return 1;
+            for (int j = 0; j <= i; ++j) hp->coef[i][j] = (float)DP_BETA[i][j] * dt_32;
+            const float si = DP_ALPHA[i] == 1.0 ? nextafterf(t1_32, t1_32 - 1.0f) : t0_32 + (float)DP_ALPHA[i] * dt_32;
+            hp->t[i] = -si;
         }
-        RkCoef ce{};
-        for (int j = 0; j < 7; ++j) ce.c[j] = dt_32 * (float)DP_CERR[j];
-        float ratio;
-        if (dp_rms(d, nullptr, nullptr, ce, y0, y1, atol_f, rtol_f, &ratio)) return 1;
-        ratio = fabsf(ratio);
+        for (int j = 0; j < 7; ++j) hp->cerr[j] = dt_32 * (float)DP_CERR[j];
+        CUDA_OK(cudaMemcpyAsync(ctx->dp_dev, hp, sizeof(DpStep), cudaMemcpyHostToDevice, s));
+        if (g_step != nullptr) {
+            CUDA_OK(cudaGraphLaunch(g_step, s));
+            ctx->launches += l_step;
+        } else if (dp_record_step(d, atol_f, rtol_f)) {
+            return 1;
+        }
+        CUDA_OK(cudaStreamSynchronize(s));  // the ONE synchronisation of the step: the controller runs on the host in fp64
+        d.nfe += 6;
+        const float ratio = fabsf(ctx->ratio_host[0]);
         const bool accept = ratio <= 1.0f;
         if (accept) {
             accepted++;
+            s_hi = t1s;
             if (t1s >= s_end) {
                 // last step: evaluate the quartic dense output at s_end and finish
                 RkCoef cm{};
@@ -1197,22 +1314,10 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
                 dopri_interp_kernel<<<blocks_for(n), 256, 0, s>>>(y0, y1, kp, cm, dt_32, xq, ytmp, n);
                 LAUNCH_OK();
                 have_interp = true;
-                s_lo = t0s;
-                s_hi = t1s;
                 break;
             }
-            s_lo = t0s;
-            s_hi = t1s;
-            dt_last = dt_32;
-            // y0 <- y1, f0 <- k7 (FSAL)
-            float* tmp = y0;
-            y0 = y1;
-            y1 = tmp;
-            float* tk = k[0];
-            k[0] = k[6];
-            k[6] = tk;
-            kp.k[0] = k[0];
-            kp.k[6] = k[6];
+            dp_accept_kernel<<<blocks_for(n), 256, 0, s>>>(y0, y1, k[0], k[6], n);  // y0 <- y1, f0 <- k7 (FSAL)
+            LAUNCH_OK();
         } else {
             rejected++;
         }
@@ -1225,12 +1330,8 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
         }
         dt = dt * factor;
     }
-    (void)s_lo;
-    (void)dt_last;
-    (void)y_prev;
     if (!have_interp) return fail(ctx, "lfm_sample_dopri5: integration produced no step");
     CUDA_OK(cudaMemcpyAsync(x_inout, ytmp, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    // restore the canonical k-buffer order for the next call
     if (join_out(ctx, user)) return 1;
     if (stats != nullptr) {
         stats->nfe = d.nfe;
@@ -1259,6 +1360,7 @@ extern "C" void lfm_destroy(lfm_ctx* ctx) {
     if (ctx->staging != nullptr) cudaFree(ctx->staging);
     delete ctx->un;
     if (ctx->ratio_host != nullptr) cudaFreeHost(ctx->ratio_host);
+    if (ctx->dp_host != nullptr) cudaFreeHost(ctx->dp_host);
     if (ctx->stream != nullptr) cudaStreamDestroy(ctx->stream);
     if (ctx->ev_in != nullptr) cudaEventDestroy(ctx->ev_in);
     if (ctx->ev_out != nullptr) cudaEventDestroy(ctx->ev_out);
