@@ -35,6 +35,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+DEFAULT_GEMM_BN = 512   # lfm_dbg_gemm tile selector of the network's default GEMM kernel (512: 256 x 256 pair tile; 640: 512 x 256)
 MODEL = "DiT-L/2"
 BATCH = 64
 NFE = 50
@@ -282,8 +283,10 @@ def gemm_vs_cublas(device, iters=20):
         gate = torch.randn(M // 256, N, device=device)
         o = torch.zeros(M, N, device=device, dtype=torch.float32 if epi >= 2 else torch.bfloat16)
 
+        bn = int(os.environ.get("LFM_BENCH_GEMM_BN", "0")) or DEFAULT_GEMM_BN
+
         def ours():
-            rc = lib.lfm_dbg_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), o.data_ptr(), gate.data_ptr(), N, 256, M, N, K, epi, 512, s)
+            rc = lib.lfm_dbg_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), o.data_ptr(), gate.data_ptr(), N, 256, M, N, K, epi, bn, s)
             assert rc == 0, _lib.last_error()
 
         def cublas():

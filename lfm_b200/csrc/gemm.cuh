@@ -45,6 +45,10 @@ struct GemmEpi {
     // produces the NEXT layer's operand  ln_out = LayerNorm(x) * (1 + ln_scale) + ln_shift  (bf16; models/DiT.py:20-21,
     // 129-130) for those rows while they are still in L2 - the stand-alone LayerNorm pass over x disappears.
     // rb_count[m_blk] counts arrivals (zero on entry; reset by the finisher).
+    // Pair kernel, EPI_BIAS_F32: out = addend + acc + bias, the residual connection of a convolutional block added by
+    // the SM (fp32 [M, ldo]; may alias out) - so that the block's OUTPUT statistics (gn_bins) can be taken in the same
+    // epilogue, which a reduce-add performed at L2 never sees.
+    const float* addend = nullptr;
     int* rb_count = nullptr;
     __nv_bfloat16* ln_out = nullptr;
     const float* ln_shift = nullptr;  // [sample * ln_stride + column]

@@ -126,10 +126,24 @@ LFM_DEVICE void tma_reduce_add_2d_hint(const CUtensorMap* m, const void* smem_sr
 
 // Epilogue math for 32 accumulator columns of one row -> f[32] (bias, GELU, gate).
 template <int EPI>
-LFM_DEVICE void epilogue_math(const uint32_t* v, float* f, const GemmEpi& ep, int n0, int N, const float* gate_row) {
+LFM_DEVICE void epilogue_math(const uint32_t* v, float* f, const GemmEpi& ep, int n0, int N, const float* gate_row,
+                              const float* add_row = nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
     if (n0 >= N) return;  // warp-uniform; the TMA store clips these columns anyway
+    if (EPI == EPI_BIAS_F32 && add_row != nullptr) {  // residual connection added here (see GemmEpi::addend)
+        const float4* ap = reinterpret_cast<const float4*>(add_row + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (n0 + j * 4 < N) {
+                const float4 a4 = __ldcg(ap + j);
+                f[4 * j + 0] += a4.x;
+                f[4 * j + 1] += a4.y;
+                f[4 * j + 2] += a4.z;
+                f[4 * j + 3] += a4.w;
+            }
+        }
+    }
     if (ep.bias != nullptr) {
         const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
 #pragma unroll
@@ -478,6 +492,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
             const float* gate_row = nullptr;
             if (EPI == EPI_GATE_RESID_F32 && ep.gate != nullptr)  // gate == nullptr: plain residual add (gate 1)
                 gate_row = ep.gate + static_cast<size_t>((row < M ? row : M - 1) / ep.rows_per_sample) * ep.gate_stride;
+            const float* add_row = nullptr;
+            if (EPI == EPI_BIAS_F32 && ep.addend != nullptr) add_row = ep.addend + static_cast<size_t>(row < M ? row : M - 1) * ep.ldo;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kG2BlockN + half * (width / 2);
@@ -488,7 +504,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
             for (int c = 0; c < nch; c += 2) {
                 tmem_ld_wait();
                 tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
-                epilogue_math<EPI>(va, f, ep, nbase + c * 32, N, gate_row);
+                epilogue_math<EPI>(va, f, ep, nbase + c * 32, N, gate_row, add_row);
                 if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + c * 32, N, lane);
                 // this staging tile is free once all but the most recent TMA op of this warp have READ their tile
                 uint8_t* stg = stg0 + sbuf * 4096;
@@ -512,7 +528,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 }
                 tmem_ld_wait();
                 if (c + 2 < nch) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
-                epilogue_math<EPI>(vb, f, ep, nbase + (c + 1) * 32, N, gate_row);
+                epilogue_math<EPI>(vb, f, ep, nbase + (c + 1) * 32, N, gate_row, add_row);
                 if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + (c + 1) * 32, N, lane);
                 if (kBf16Out) {
                     stage_row_bf16_half(stg, lane, f, 1);

@@ -21,6 +21,7 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "gemm4.cuh"
+#include "gemm5.cuh"
 #include "kernels.cuh"
 #include "unet.cuh"
 #include "vae.cuh"
@@ -189,6 +190,42 @@ static cudaError_t launch_gemm2_fin(cudaStream_t s, const CUtensorMap& ta, const
                     (tbh != nullptr && split_env) ? 1 : 0, 1, 0);
 }
 
+// Pair kernel with the 512 x 256 cluster tile (gemm5.cuh)
+static G5Sched g5_schedule_host(int M, int N, int clusters) {
+    G5Sched s;
+    s.n_blocks = (N + 255) / 256;
+    s.m512 = (M + 511) / 512;
+    const int tiles = s.m512 * s.n_blocks;
+    s.full_count = (tiles / clusters) * clusters;
+    const int rem = tiles - s.full_count;
+    s.split = 1;
+    if (rem > 0) {
+        int best_num = (rem + clusters - 1) / clusters * 4, best = 1;
+        for (int f = 2; f <= 4; f *= 2) {
+            const int c = ((rem * f + clusters - 1) / clusters) * (4 / f);
+            if (c < best_num) {
+                best_num = c;
+                best = f;
+            }
+        }
+        s.split = best;
+    }
+    s.num_items = s.full_count + rem * s.split;
+    return s;
+}
+template <int EPI>
+static cudaError_t launch_gemm5_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                                     const CUtensorMap& tbh, int M, int N, int K, const GemmEpi& ep,
+                                     ConvGeom cg = ConvGeom{0, 0, 0, 0, 1}) {
+    static DevOnce once;
+    auto kern = gemm5_bf16_tcgen05<EPI>;
+    if (cudaError_t e = smem_opt_in(once, kern, kG5SmemBytes)) return e;
+    const int sched_clusters = g_num_sms / 2;
+    const G5Sched sc = g5_schedule_host(M, N, sched_clusters);
+    const int clusters = sc.num_items < sched_clusters ? sc.num_items : sched_clusters;
+    return launch_k(kern, dim3(2 * clusters), kG5Threads, kG5SmemBytes, s, ta, tb, tout, tbh, M, N, K, ep, cg, sched_clusters);
+}
+
 // 4-CTA cluster kernel (two pairs sharing A by multicast; 256 x 512 block per cluster)
 template <int EPI>
 static cudaError_t launch_gemm4_inst(cudaStream_t s, const CUtensorMap& ta64, const CUtensorMap& tb, const CUtensorMap& tout,
@@ -230,7 +267,10 @@ static cudaError_t launch_gemm4_inst(cudaStream_t s, const CUtensorMap& ta64, co
 // kGemmQuad (1024) = cluster of two pairs per 256 x 512 block (A multicast)
 constexpr int kGemmPair = 512;
 constexpr int kGemmQuad = 1024;
-static inline uint32_t weight_box_rows(int block_n) { return (block_n == kGemmPair || block_n == kGemmQuad) ? 128u : static_cast<uint32_t>(block_n); }
+constexpr int kGemmPair512 = 640;  // CTA pair per 512 x 256 tile (gemm5.cuh)
+static inline uint32_t weight_box_rows(int block_n) {
+    return (block_n == kGemmPair || block_n == kGemmQuad || block_n == kGemmPair512) ? 128u : static_cast<uint32_t>(block_n);
+}
 
 static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                                int epi, int block_n, const GemmEpi& ep, const CUtensorMap* tout = nullptr,
@@ -241,6 +281,14 @@ static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUte
         if (epi == EPI_BIAS_GELU_BF16) return launch_gemm4_inst<EPI_BIAS_GELU_BF16>(s, *ta64, tb, *tout, M, N, K, ep);
         if (epi == EPI_GATE_RESID_F32) return launch_gemm4_inst<EPI_GATE_RESID_F32>(s, *ta64, tb, *tout, M, N, K, ep);
         if (epi == EPI_BIAS_F32) return launch_gemm4_inst<EPI_BIAS_F32>(s, *ta64, tb, *tout, M, N, K, ep);
+        return cudaErrorInvalidValue;
+    }
+    if (block_n == kGemmPair512) {
+        if (tout == nullptr || tbh == nullptr) return cudaErrorInvalidValue;
+        if (epi == EPI_BIAS_BF16) return launch_gemm5_inst<EPI_BIAS_BF16>(s, ta, tb, *tout, *tbh, M, N, K, ep);
+        if (epi == EPI_BIAS_GELU_BF16) return launch_gemm5_inst<EPI_BIAS_GELU_BF16>(s, ta, tb, *tout, *tbh, M, N, K, ep);
+        if (epi == EPI_GATE_RESID_F32) return launch_gemm5_inst<EPI_GATE_RESID_F32>(s, ta, tb, *tout, *tbh, M, N, K, ep);
+        if (epi == EPI_BIAS_F32) return launch_gemm5_inst<EPI_BIAS_F32>(s, ta, tb, *tout, *tbh, M, N, K, ep);
         return cudaErrorInvalidValue;
     }
     if (block_n == kGemmPair) {
@@ -487,7 +535,7 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     ctx->attn_variant = env_int("LFM_ATTN_VARIANT", 3);
     ctx->zigzag = env_int("LFM_ZIGZAG", 1);
     ctx->l2_hint = env_int("LFM_L2_HINT", 0);
-    ctx->ln_fuse = env_int("LFM_LN_FUSE", 1);
+    ctx->ln_fuse = env_int("LFM_LN_FUSE", 0);  // measured (r2b): the in-kernel LayerNorm finisher is 2.6x SLOWER end to end - off
     const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
 
     if (dev_alloc(ctx, &ctx->pos, (size_t)T * D)) return 1;
@@ -600,7 +648,7 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
 
 static int pick_bn(int N, const char* env, int dflt) {
     int bn = env_int(env, dflt);
-    if (bn != 128 && bn != 256 && bn != kGemmPair && bn != kGemmQuad) bn = dflt;
+    if (bn != 128 && bn != 256 && bn != kGemmPair && bn != kGemmQuad && bn != kGemmPair512) bn = dflt;
     return bn;
 }
 
@@ -755,7 +803,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
     };
     // LayerNorm fusion: the proj / fc2 GEMMs (pair kernel, full rows: N == D) also emit the LayerNorm-modulated operand of
     // the layer that follows them; only the very first LayerNorm of the network is a stand-alone pass.
-    const bool fuse = ctx->ln_fuse && ctx->bn_proj == kGemmPair && ctx->bn_fc2 == kGemmPair;
+    const bool fuse = ctx->ln_fuse && ctx->bn_proj == kGemmPair && ctx->bn_fc2 == kGemmPair;  // (the finisher lives in gemm2 only)
     for (int l = 0; l < L; ++l) {
         BlockW& b = ctx->blk[l];
         const float* mb = ctx->mod + (size_t)l * 6 * D;  // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
@@ -1375,8 +1423,8 @@ extern "C" int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float*
                             void* stream) {
     lfm_ctx* ctx = nullptr;
     if (K % 64 != 0 || N % 8 != 0) return fail(ctx, "lfm_dbg_gemm: K must be a multiple of 64 and N of 8");
-    if (block_n != 128 && block_n != 256 && block_n != kGemmPair && block_n != kGemmQuad)
-        return fail(ctx, "lfm_dbg_gemm: block_n must be 128, 256, 512 (CTA pair) or 1024 (4-CTA cluster)");
+    if (block_n != 128 && block_n != 256 && block_n != kGemmPair && block_n != kGemmQuad && block_n != kGemmPair512)
+        return fail(ctx, "lfm_dbg_gemm: block_n must be 128, 256, 512 (CTA pair), 640 (CTA pair, 512 x 256 tile) or 1024 (4-CTA cluster)");
     g_num_sms = query_num_sms();
     if (g_num_sms <= 0) return fail(ctx, "no CUDA device");
     CUtensorMap ta, tb;

@@ -144,32 +144,59 @@ def rename_legacy_keys(sd):
     return out
 
 
+# Optional emulation of the CUDA path's operand rounding (vae_decode(..., emulate_bf16=True)): the operands of every
+# tensor-core contraction (all convolutions but the 4-channel conv_in / post_quant_conv, the attention projections and
+# the two attention matmuls) are rounded to bf16; accumulation, GroupNorm, SiLU, softmax and the residual stream stay fp32.
+# With random (synthetic) weights the decoder amplifies operand rounding to ~1.5e-2 relative at the output; the tests
+# use this mode to separate that inherent noise from implementation error.  Default False = the fp32 restatement.
+_EMULATE_BF16 = False
+
+
+def _r(t):
+    return t.bfloat16().float() if _EMULATE_BF16 else t
+
+
+def _conv(x, w, b, **kw):
+    return F.conv2d(_r(x), _r(w), b, **kw)
+
+
+def _lin(x, w, b):
+    return F.linear(_r(x), _r(w), b)
+
+
 def _gn(x, sd, p, cfg):
     return F.group_norm(x, cfg.norm_num_groups, sd[p + ".weight"], sd[p + ".bias"], eps=cfg.eps)
 
 
 def resnet_block(sd, p, x, cfg):
-    h = F.conv2d(F.silu(_gn(x, sd, p + ".norm1", cfg)), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
-    h = F.conv2d(F.silu(_gn(h, sd, p + ".norm2", cfg)), sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
+    h = _conv(F.silu(_gn(x, sd, p + ".norm1", cfg)), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
+    h = _conv(F.silu(_gn(h, sd, p + ".norm2", cfg)), sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
     if p + ".conv_shortcut.weight" in sd:
-        x = F.conv2d(x, sd[p + ".conv_shortcut.weight"], sd[p + ".conv_shortcut.bias"])
+        x = _conv(x, sd[p + ".conv_shortcut.weight"], sd[p + ".conv_shortcut.bias"])
     return x + h
 
 
 def attention_block(sd, p, x, cfg):
     B, C, H, W = x.shape
     h = _gn(x, sd, p + ".group_norm", cfg).reshape(B, C, H * W).transpose(1, 2)
-    q = F.linear(h, sd[p + ".to_q.weight"], sd[p + ".to_q.bias"])
-    k = F.linear(h, sd[p + ".to_k.weight"], sd[p + ".to_k.bias"])
-    v = F.linear(h, sd[p + ".to_v.weight"], sd[p + ".to_v.bias"])
-    a = torch.softmax(q @ k.transpose(1, 2) * (1.0 / math.sqrt(C)), dim=-1) @ v       # one head of C channels
-    a = F.linear(a, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
+    q = _r(_lin(h, sd[p + ".to_q.weight"], sd[p + ".to_q.bias"]))
+    k = _r(_lin(h, sd[p + ".to_k.weight"], sd[p + ".to_k.bias"]))
+    v = _r(_lin(h, sd[p + ".to_v.weight"], sd[p + ".to_v.bias"]))
+    a = _r(torch.softmax(q @ k.transpose(1, 2) * (1.0 / math.sqrt(C)), dim=-1)) @ v   # one head of C channels
+    a = _lin(a, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
     return a.transpose(1, 2).reshape(B, C, H, W) + x
 
 
 @torch.no_grad()
-def vae_decode(sd, z, cfg: VAEConfig = VAEConfig(), return_features: bool = False):
+def vae_decode(sd, z, cfg: VAEConfig = VAEConfig(), return_features: bool = False, emulate_bf16: bool = False):
     """``AutoencoderKL.decode(z).sample``: z [B, 4, h, w] fp32 -> [B, 3, 8h, 8w] fp32."""
+    global _EMULATE_BF16
+    if emulate_bf16:
+        _EMULATE_BF16 = True
+        try:
+            return vae_decode(sd, z, cfg, return_features)
+        finally:
+            _EMULATE_BF16 = False
     plan, _, _ = decoder_plan(cfg)
     h = F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
     h = F.conv2d(h, sd["decoder.conv_in.weight"], sd["decoder.conv_in.bias"], padding=1)
@@ -181,11 +208,11 @@ def vae_decode(sd, z, cfg: VAEConfig = VAEConfig(), return_features: bool = Fals
             h = attention_block(sd, p, h, cfg)
         else:
             h = F.interpolate(h, scale_factor=2.0, mode="nearest")
-            h = F.conv2d(h, sd[p + ".conv.weight"], sd[p + ".conv.bias"], padding=1)
+            h = _conv(h, sd[p + ".conv.weight"], sd[p + ".conv.bias"], padding=1)
         if return_features:
             feats.append((p, h))
     h = F.silu(_gn(h, sd, "decoder.conv_norm_out", cfg))
-    out = F.conv2d(h, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
+    out = _conv(h, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
     return (out, feats) if return_features else out
 
 

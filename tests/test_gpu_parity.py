@@ -66,7 +66,11 @@ def make_big(model_type, dev, num_classes, label_dropout, max_batch):
     (256, 1152, 384, 1, 128), (16384, 3072, 1024, 0, 256), (16384, 1024, 1024, 2, 128),
     # CTA-pair kernel (512) incl. tail splitting / N tails, and the 4-CTA multicast kernel (1024)
     (256, 256, 64, 3, 512), (768, 1152, 384, 0, 512), (512, 1024, 4096, 2, 512), (16384, 1024, 4096, 2, 512),
-    (16384, 3072, 1024, 1, 512), (768, 768, 384, 1, 1024), (512, 1024, 4096, 2, 1024), (16384, 3072, 1024, 0, 1024)])
+    (16384, 3072, 1024, 1, 512), (768, 768, 384, 1, 1024), (512, 1024, 4096, 2, 1024), (16384, 3072, 1024, 0, 1024),
+    # CTA-pair kernel with the 512 x 256 cluster tile (640): whole tiles, half / quarter tail tiles, M and N tails, M < 512
+    (512, 256, 64, 3, 640), (256, 256, 128, 3, 640), (768, 1152, 384, 0, 640), (1280, 768, 256, 1, 640), (512, 1024, 4096, 2, 640),
+    (4096, 1024, 1024, 2, 640), (16384, 1024, 4096, 2, 640), (16384, 3072, 1024, 1, 640), (16384, 4096, 1024, 0, 640),
+    (32768, 1024, 1024, 2, 640), (38 * 512, 512, 128, 3, 640)])
 def test_gemm_epilogues(dev, M, N, K, epi, bn):
     lib = _lib.load()
     g = torch.Generator().manual_seed(M + N + K + epi)
@@ -577,7 +581,12 @@ def test_edm_unsupported_configuration_fails_loudly(dev):
 
 # ------------------------------------------------------------------------------------------------ VAE decode
 
-TOL_VAE = 1e-2   # ~30 bf16-operand convolutions + one attention per decode, no small gates (same budget as the UNets)
+# ~30 bf16-operand convolutions + one attention per decode.  With the random synthetic weights the decoder amplifies the
+# rounding of the tensor-core operands to 1.5e-2 at the output (oracle/vae.py emulate_bf16 reproduces exactly that figure
+# on the CPU), so the check against the fp32 restatement is 3e-2 and the sharp check is against the same arithmetic
+# with bf16-rounded operands: what is left there is accumulation order and GroupNorm statistics (measured ~3e-3).
+TOL_VAE = 3e-2
+TOL_VAE_EMU = 8e-3
 
 
 def make_vae(dev, seed=1, max_batch=4):
@@ -602,6 +611,7 @@ def test_vae_decode_vs_oracle(dev, side, B):
     assert out.shape == (B, 3, 8 * side, 8 * side) and torch.isfinite(out).all()
     ref = ovae.vae_decode(sd, z)
     assert rel_l2(out.cpu(), ref) < TOL_VAE
+    assert rel_l2(out.cpu(), ovae.vae_decode(sd, z, emulate_bf16=True)) < TOL_VAE_EMU
     assert torch.equal(out, vae.decode(z.to(dev)).sample)                  # deterministic
     assert rel_l2(vae.decode(z[:1].to(dev)).sample.cpu(), out[:1].cpu()) < 1e-5   # samples are independent
     # fused post-processing == the reference's expression applied to the native sample, bit for bit

@@ -270,7 +270,7 @@ def time_gemm(M, N, K, epi, bn, iters=20):
 def group_perf():
     for M in (16384, 32768, 4096):
         for (N, K, epi) in ((3072, 1024, 0), (1024, 1024, 2), (4096, 1024, 1), (1024, 4096, 2)):
-            for bn in (512, 256):
+            for bn in (640, 512):
                 time_gemm(M, N, K, epi, bn)
     # cuBLAS reference for the same shapes
     for (M, N, K) in ((16384, 3072, 1024), (16384, 1024, 1024), (16384, 4096, 1024), (16384, 1024, 4096)):
