@@ -223,7 +223,9 @@ static cudaError_t launch_gemm5_inst(cudaStream_t s, const CUtensorMap& ta, cons
     const int sched_clusters = g_num_sms / 2;
     const G5Sched sc = g5_schedule_host(M, N, sched_clusters);
     const int clusters = sc.num_items < sched_clusters ? sc.num_items : sched_clusters;
-    return launch_k(kern, dim3(2 * clusters), kG5Threads, kG5SmemBytes, s, ta, tb, tout, tbh, M, N, K, ep, cg, sched_clusters);
+    static const int skew = std::min(std::max(env_int("LFM_G5_SKEW", kG5Skew), 0), kG5Skew);
+    static const int dbg = env_int("LFM_G5_DBG", 0);
+    return launch_k(kern, dim3(2 * clusters), kG5Threads, kG5SmemBytes, s, ta, tb, tout, tbh, M, N, K, ep, cg, sched_clusters, skew, dbg);
 }
 
 // 4-CTA cluster kernel (two pairs sharing A by multicast; 256 x 512 block per cluster)

@@ -267,6 +267,11 @@ def time_gemm(M, N, K, epi, bn, iters=20):
     print(f"  gemm M={M} N={N} K={K} epi={epi} bn={bn}: {ms*1e3:8.1f} us  {2*M*N*K/ms/1e9:8.1f} TFLOP/s", flush=True)
 
 
+def group_perf16k():
+    for (N, K, epi) in ((3072, 1024, 0), (1024, 1024, 2), (4096, 1024, 1), (1024, 4096, 2)):
+        time_gemm(16384, N, K, epi, 640)
+
+
 def group_perf():
     for M in (16384, 32768, 4096):
         for (N, K, epi) in ((3072, 1024, 0), (1024, 1024, 2), (4096, 1024, 1), (1024, 4096, 2)):
@@ -290,5 +295,5 @@ if __name__ == "__main__":
     grp = sys.argv[1]
     print(f"=== {grp} ===", flush=True)
     t = time.time()
-    {"gemm": group_gemm, "attn": group_attn, "forward": group_forward, "sampler": group_sampler, "perf": group_perf, "unet": group_unet, "gemm4": group_gemm4}[grp]()
+    {"gemm": group_gemm, "attn": group_attn, "forward": group_forward, "sampler": group_sampler, "perf": group_perf, "unet": group_unet, "gemm4": group_gemm4, "perf16k": group_perf16k}[grp]()
     print(f"=== {grp} done in {time.time()-t:.1f}s ===", flush=True)
