@@ -231,6 +231,41 @@ LFM_DEVICE float gelu_tanh(float x) {
     const float hx = 0.5f * x;
     return fmaf(hx, tanh_fast(inner), hx);
 }
+// GELU(tanh) of two values at once with Blackwell's packed fp32 arithmetic (fma / mul .f32x2: one issue slot per PAIR):
+// 5 packed operations + 2 MUFU.TANH instead of 10 scalar operations + 2 MUFU.  Same formula, same fp32 precision.
+LFM_DEVICE void gelu_tanh_x2(float& a, float& b) {
+    const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+    uint64_t x, x2, ic, in, hx, o, K0, K0K1, HALF;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(K0) : "f"(k0));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(K0K1) : "f"(k0k1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(HALF) : "f"(0.5f));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(x2) : "l"(x));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ic) : "l"(K0K1), "l"(x2), "l"(K0));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(in) : "l"(x), "l"(ic));
+    float i0, i1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(i0), "=f"(i1) : "l"(in));
+    const float t0 = tanh_fast(i0), t1 = tanh_fast(i1);
+    uint64_t t;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hx) : "l"(x), "l"(HALF));
+    asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(o) : "l"(hx), "l"(t));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(o));
+}
+LFM_DEVICE void add_x2(float& a, float& b, float c, float d) {  // (a, b) += (c, d) in one packed instruction
+    uint64_t x, y;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(c), "f"(d));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x));
+}
+LFM_DEVICE void mul_x2(float& a, float& b, float c, float d) {  // (a, b) *= (c, d)
+    uint64_t x, y;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(c), "f"(d));
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x));
+}
 LFM_DEVICE float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 LFM_DEVICE float warp_sum(float v) {

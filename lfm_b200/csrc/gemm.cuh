@@ -49,6 +49,7 @@ struct GemmEpi {
     // the SM (fp32 [M, ldo]; may alias out) - so that the block's OUTPUT statistics (gn_bins) can be taken in the same
     // epilogue, which a reduce-add performed at L2 never sees.
     const float* addend = nullptr;
+    int dbg_flags = 0;  // measurement aids (LFM_G2_DBG): 1 = the epilogue releases the accumulator without draining it
     int* rb_count = nullptr;
     __nv_bfloat16* ln_out = nullptr;
     const float* ln_shift = nullptr;  // [sample * ln_stride + column]

@@ -53,6 +53,13 @@ LFM_DEVICE void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* 
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1)
         : "memory");
 }
+LFM_DEVICE void tma_load_2d_2sm_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, uint64_t policy) {
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 // 4-D variant (NHWC activation tensor {C, W, H, B}): the im2col gather of one filter tap is a shifted box;
 // out-of-bounds rows/columns (the zero padding) are zero-filled by TMA.
 LFM_DEVICE void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2,
@@ -150,16 +157,14 @@ LFM_DEVICE void epilogue_math(const uint32_t* v, float* f, const GemmEpi& ep, in
         for (int j = 0; j < 8; ++j) {
             if (n0 + j * 4 < N) {
                 const float4 b4 = __ldg(bp + j);
-                f[4 * j + 0] += b4.x;
-                f[4 * j + 1] += b4.y;
-                f[4 * j + 2] += b4.z;
-                f[4 * j + 3] += b4.w;
+                add_x2(f[4 * j + 0], f[4 * j + 1], b4.x, b4.y);
+                add_x2(f[4 * j + 2], f[4 * j + 3], b4.z, b4.w);
             }
         }
     }
     if (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+        for (int j = 0; j < 32; j += 2) gelu_tanh_x2(f[j], f[j + 1]);
     }
     if (EPI == EPI_GATE_RESID_F32 && gate_row != nullptr) {
         const float4* gp = reinterpret_cast<const float4*>(gate_row + n0);
@@ -167,10 +172,8 @@ LFM_DEVICE void epilogue_math(const uint32_t* v, float* f, const GemmEpi& ep, in
         for (int j = 0; j < 8; ++j) {
             if (n0 + j * 4 < N) {
                 const float4 g4 = __ldg(gp + j);
-                f[4 * j + 0] *= g4.x;
-                f[4 * j + 1] *= g4.y;
-                f[4 * j + 2] *= g4.z;
-                f[4 * j + 3] *= g4.w;
+                mul_x2(f[4 * j + 0], f[4 * j + 1], g4.x, g4.y);
+                mul_x2(f[4 * j + 2], f[4 * j + 3], g4.z, g4.w);
             }
         }
     }
@@ -291,6 +294,23 @@ LFM_DEVICE void ln_finish_rows(const GemmEpi& ep, int row0, int nrows, int M, in
     }
 }
 
+// bf16 output of one lane's 32-column row segment straight from registers (64 contiguous bytes, two full 32-byte
+// sectors): no shared-memory staging, no TMA store - the pair kernel's mainloop already uses ~125 of the 128 B/clk of
+// shared-memory bandwidth, and every staged byte (write + TMA read-back) extends the kernel (profiles/r2g_gemm2_epilogue_cost.md).
+LFM_DEVICE void store_row_bf16_direct(__nv_bfloat16* rowp /* out + row * ldo + n0 */, const float* f, int n0, int N) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (n0 + 8 * j < N) {
+            uint4 o;
+            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            *reinterpret_cast<uint4*>(rowp + 8 * j) = o;
+        }
+    }
+}
+
 template <int EPI, bool FIN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FIN ? kG2ThreadsFin : kG2Threads, 1)
 gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], box {64, 128}
@@ -389,6 +409,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // l2_keep (LFM_L2_HINT): the A operand of a residual GEMM is streamed once - mark it evict_first so that it does
+            // not push the fp32 residual stream (re-read by the LayerNorm that follows) out of the L2
+            const uint64_t a_policy = (EPI == EPI_GATE_RESID_F32 && ep.l2_keep) ? l2_policy_evict_first() : 0;
             for (int item = cluster_id; item < num_items; item += num_clusters) {
                 int m_blk, n_blk, nh, width;
                 decode(item, m_blk, n_blk, nh, width);
@@ -415,7 +438,10 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     if (cg.taps == 0) {
-                        tma_load_2d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * 64, row_a);
+                        if (a_policy != 0)
+                            tma_load_2d_2sm_hint(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * 64, row_a, a_policy);
+                        else
+                            tma_load_2d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * 64, row_a);
                     } else {
                         const int r = tap / 3, sx = tap - 3 * r;
                         tma_load_4d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], cb * 64, cg.stride * w0 + sx - 1,
@@ -496,18 +522,47 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
             if (EPI == EPI_BIAS_F32 && ep.addend != nullptr) add_row = ep.addend + static_cast<size_t>(row < M ? row : M - 1) * ep.ldo;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
+            if (ep.dbg_flags & 1) {  // measurement aid: mainloop speed without any TMEM drain (results are not written)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kG2BlockN + half * (width / 2);
             uint32_t va[32], vb[32];
             float f[32];
             tmem_ld_32x32b_x32(taddr, va);
+            const bool direct_bf16 = (ep.dbg_flags & 8) != 0;    // bf16 outputs: registers -> global, no staging (A/B switch)
+            const bool dbg_no_math = (ep.dbg_flags & 2) != 0;    // measurement aid: TMEM is read, nothing else happens
+            const bool dbg_no_store = (ep.dbg_flags & 4) != 0;   // measurement aid: everything but the global stores
 #pragma unroll 1
             for (int c = 0; c < nch; c += 2) {
                 tmem_ld_wait();
                 tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
+                if (dbg_no_math) {
+                    tmem_ld_wait();
+                    if (c + 2 < nch) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
+                    if (__uint_as_float(va[0] ^ vb[1]) == 1.2345e-31f) stg0[lane] = 1;  // keep the loads alive
+                    continue;
+                }
                 epilogue_math<EPI>(va, f, ep, nbase + c * 32, N, gate_row, add_row);
                 if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + c * 32, N, lane);
                 // this staging tile is free once all but the most recent TMA op of this warp have READ their tile
                 uint8_t* stg = stg0 + sbuf * 4096;
+                if (kBf16Out && direct_bf16) {
+                    if (row < M && ksplit == 1)
+                        store_row_bf16_direct(static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ldo + nbase + c * 32, f, nbase + c * 32, N);
+                    tmem_ld_wait();
+                    if (c + 2 < nch) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
+                    epilogue_math<EPI>(vb, f, ep, nbase + (c + 1) * 32, N, gate_row, add_row);
+                    if (row < M && ksplit == 1)
+                        store_row_bf16_direct(static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(row) * ep.ldo + nbase + (c + 1) * 32, f, nbase + (c + 1) * 32, N);
+                    continue;
+                }
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
                 if (kBf16Out) {
@@ -516,7 +571,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     stage_row_f32(stg, lane, f);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && nbase + c * 32 < N) {
+                    if (lane == 0 && nbase + c * 32 < N && !dbg_no_store) {
                         if (EPI == EPI_GATE_RESID_F32 && ep.l2_keep)
                             tma_reduce_add_2d_hint(&tmap_out, stg, nbase + c * 32, row0, keep_policy);
                         else if (EPI == EPI_GATE_RESID_F32)
@@ -534,7 +589,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     stage_row_bf16_half(stg, lane, f, 1);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && nbase + c * 32 < N) tma_store_2d(&tmap_out, stg, nbase + c * 32, row0);  // 64 bf16 cols
+                    if (lane == 0 && nbase + c * 32 < N && !dbg_no_store) tma_store_2d(&tmap_out, stg, nbase + c * 32, row0);  // 64 bf16 cols
                     if (lane == 0) tma_store_commit();
                 } else {
                     stg = stg0 + sbuf * 4096;
@@ -543,7 +598,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     stage_row_f32(stg, lane, f);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && nbase + (c + 1) * 32 < N) {
+                    if (lane == 0 && nbase + (c + 1) * 32 < N && !dbg_no_store) {
                         if (EPI == EPI_GATE_RESID_F32 && ep.l2_keep)
                             tma_reduce_add_2d_hint(&tmap_out, stg, nbase + (c + 1) * 32, row0, keep_policy);
                         else if (EPI == EPI_GATE_RESID_F32)

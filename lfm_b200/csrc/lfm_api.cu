@@ -806,6 +806,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
     // LayerNorm fusion: the proj / fc2 GEMMs (pair kernel, full rows: N == D) also emit the LayerNorm-modulated operand of
     // the layer that follows them; only the very first LayerNorm of the network is a stand-alone pass.
     const bool fuse = ctx->ln_fuse && ctx->bn_proj == kGemmPair && ctx->bn_fc2 == kGemmPair;  // (the finisher lives in gemm2 only)
+    static const int g2_flags = env_int("LFM_G2_FLAGS", 0) & 8;  // 8: bf16 epilogues store straight from registers (A/B switch)
     for (int l = 0; l < L; ++l) {
         BlockW& b = ctx->blk[l];
         const float* mb = ctx->mod + (size_t)l * 6 * D;  // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
@@ -816,6 +817,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         }
         {
             GemmEpi ep{b.b_qkv, ctx->qkv, 3 * D, nullptr, 0, T};
+            ep.dbg_flags = g2_flags;
             ep.reverse_m = next_dir();
             CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv, &b.tmh_qkv, &ctx->tm64_xn));
             ctx->launches++;
@@ -851,6 +853,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         }
         {
             GemmEpi ep{b.b_fc1, ctx->hmid, Hd, nullptr, 0, T};
+            ep.dbg_flags = g2_flags;
             ep.reverse_m = next_dir();
             CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_fc1, M, Hd, D, EPI_BIAS_GELU_BF16, ctx->bn_fc1, ep, &ctx->tmo_hmid, &b.tmh_fc1, &ctx->tm64_xn));
             ctx->launches++;
@@ -1433,6 +1436,7 @@ extern "C" int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float*
     if (!make_tmap_bf16(&ta, a_bf16, M, K, 128) || !make_tmap_bf16(&tb, w_bf16, N, K, weight_box_rows(block_n)))
         return fail(ctx, "lfm_dbg_gemm: tensor map encode failed");
     GemmEpi ep{bias, out, N, gate, gate_stride, rows_per_sample > 0 ? rows_per_sample : 1};
+    ep.dbg_flags = env_int("LFM_G2_DBG", 0);
     CUtensorMap tout;
     if (!make_tmap_out(&tout, out, M, N, epi >= 2)) return fail(ctx, "lfm_dbg_gemm: output tensor map encode failed");
     CUtensorMap tbh;

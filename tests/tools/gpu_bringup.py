@@ -268,8 +268,9 @@ def time_gemm(M, N, K, epi, bn, iters=20):
 
 
 def group_perf16k():
+    bn = int(os.environ.get("LFM_PERF_BN", "640"))
     for (N, K, epi) in ((3072, 1024, 0), (1024, 1024, 2), (4096, 1024, 1), (1024, 4096, 2)):
-        time_gemm(16384, N, K, epi, 640)
+        time_gemm(16384, N, K, epi, bn)
 
 
 def group_perf():
