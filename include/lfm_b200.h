@@ -28,6 +28,10 @@ typedef struct lfm_ctx lfm_ctx;
 enum { LFM_ARCH_DIT = 0, LFM_ARCH_UNET = 1 };
 enum { LFM_DTYPE_F32 = 0 };
 enum { LFM_METHOD_EULER = 0, LFM_METHOD_HEUN = 1, LFM_METHOD_MIDPOINT = 2, LFM_METHOD_RK4 = 3 };
+/* bits of lfm_sample_fixed's `t_as_vector` argument */
+enum { LFM_FIXED_T_VECTOR = 1, LFM_FIXED_PERTURB = 2 };
+/* torchdiffeq's adaptive Runge-Kutta pairs (test_flow_latent.py:27 ADAPTIVE_SOLVER; dopri8 is not implemented) */
+enum { LFM_ADAPTIVE_DOPRI5 = 0, LFM_ADAPTIVE_BOSH3 = 1, LFM_ADAPTIVE_HEUN = 2 };
 
 /* Constructor arguments of the reference network (models/DiT.py:157-169, selected by
  * models/__init__.py:12-17 create_network).  image side = grid * patch. */
@@ -155,7 +159,9 @@ int lfm_forward(lfm_ctx* ctx, const float* t, int t_numel, const float* x, const
  *                                                                   sampler/karras_sample.py:122-161
  *   LFM_METHOD_MIDPOINT / LFM_METHOD_RK4   torchdiffeq's fixed-grid midpoint and rk4 (3/8 rule) step functions
  *                                                                   (test_flow_latent.py:61-73 with --method midpoint|rk4)
- *   t_as_vector: 0 = the model sees a 0-d t (torchdiffeq), 1 = a [B] vector (Karras samplers).
+ *   t_as_vector: bit 0 (LFM_FIXED_T_VECTOR): 0 = the model sees a 0-d t (torchdiffeq), 1 = a [B] vector (Karras samplers);
+ *   bit 1 (LFM_FIXED_PERTURB): torchdiffeq options["perturb"] = True (test_flow_latent.py:44-48,64): the first evaluation of
+ *   every step sees t one fp32 ulp past the node, rk4's last one one ulp before the next node.
  *   x_inout: [B_img, C, H, W] latents, updated in place.  y: labels, [B_img] (cfg_scale <= 1) or [2*B_img]
  *   (cfg_scale > 1: conditional labels then null labels; a 2*B_img-row network batch is evaluated per NFE).
  *   The whole trajectory runs from a captured CUDA graph; no host synchronisation between steps. */
@@ -167,6 +173,12 @@ int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const float* t_gr
  * whole batch, fp64 time, dense output at t1)        test_flow_latent.py:42-76 with --method dopri5. */
 int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double t1, double rtol, double atol, const int64_t* y,
                       int B_img, float cfg_scale, lfm_ode_stats* stats, void* stream);
+
+/* The same controller with another embedded pair: --method dopri5 | bosh3 | adaptive_heun (test_flow_latent.py:27,61-73;
+ * torchdiffeq rk_common.RKAdaptiveStepsizeODESolver: initial step with order - 1, step factor with order, y1 / f1 / dense
+ * output as in its _runge_kutta_step / _interp_fit).  lfm_sample_dopri5 == lfm_sample_adaptive(LFM_ADAPTIVE_DOPRI5). */
+int lfm_sample_adaptive(lfm_ctx* ctx, int method, float* x_inout, double t0, double t1, double rtol, double atol,
+                        const int64_t* y, int B_img, float cfg_scale, lfm_ode_stats* stats, void* stream);
 
 const char* lfm_last_error(const lfm_ctx* ctx);
 void lfm_destroy(lfm_ctx* ctx);

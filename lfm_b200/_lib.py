@@ -53,6 +53,8 @@ SYMBOLS = {
                                    C.POINTER(OdeStats), _P]),
     "lfm_sample_dopri5": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, _P, C.c_int, C.c_float,
                                     C.POINTER(OdeStats), _P]),
+    "lfm_sample_adaptive": (C.c_int, [_P, C.c_int, _P, C.c_double, C.c_double, C.c_double, C.c_double, _P, C.c_int, C.c_float,
+                                      C.POINTER(OdeStats), _P]),
     "lfm_last_error": (C.c_char_p, [_P]),
     "lfm_destroy": (None, [_P]),
     "lfm_launch_count": (C.c_int64, [_P]),

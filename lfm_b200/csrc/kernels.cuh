@@ -376,12 +376,18 @@ __global__ void cfg_combine_kernel(const float* __restrict__ v_net, float* __res
 struct StepState {
     int step;         // current interval index i
     int n_intervals;  // len(t_grid) - 1
+    int perturb;      // torchdiffeq options["perturb"]: the step's first evaluation sees t one fp32 ulp past the node
 };
 
 // Writes the model time(s) for the next evaluation: t_eval[0] = t_grid[step + which] (which: 0 = t_cur, 1 = t_next)
 __global__ void step_time_kernel(const float* __restrict__ t_grid, const StepState* __restrict__ st, int which,
                                  float* __restrict__ t_eval) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) t_eval[0] = t_grid[st->step + which];
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float t = t_grid[st->step + which];
+        // Perturb.NEXT in torchdiffeq's negated time s = -t (nextafter(s, s + 1)) = one ulp DOWN in model time
+        if (st->perturb && which == 0) t = nextafterf(t, t - 1.0f);
+        t_eval[0] = t;
+    }
 }
 
 // Euler:  x <- x + v * (sign * (t[i+1] - t[i]))      (karras_sample.py:116-117; torchdiffeq y0 + dt*f with the

@@ -1000,7 +1000,7 @@ static int get_step_graph(lfm_ctx* ctx, int kind, int n_img, bool has_y, float c
     if (record_step(ctx, kind, n_img, has_y, cfg_scale)) return 1;
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
     const int launches_per_replay = static_cast<int>(ctx->launches - launches_before);
-    StepState zero{0, 0};
+    StepState zero{0, 0, 0};
     // (the warm-up advanced the device step counter and state; callers re-initialise both afterwards)
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -1023,7 +1023,9 @@ static int get_step_graph(lfm_ctx* ctx, int kind, int n_img, bool has_y, float c
 extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const float* t_grid_host, int n_grid,
                                 int t_as_vector, int heun_corrector_limit, const int64_t* y, int B_img, float cfg_scale,
                                 lfm_ode_stats* stats, void* stream) {
-    (void)t_as_vector;  // a [B] vector of equal times and a 0-d time give the same conditioning vector
+    // bit 0 (t as a [B] vector): a vector of equal times and a 0-d time give the same conditioning vector - nothing to do
+    const int perturb = (t_as_vector & LFM_FIXED_PERTURB) ? 1 : 0;
+    if (perturb && method == LFM_METHOD_HEUN) return fail(ctx, "lfm_sample_fixed: perturb applies to the torchdiffeq grids (euler, midpoint, rk4)");
     const int rows = cfg_scale > 1.0f ? 2 * B_img : B_img;
     if (check_ready(ctx, rows, "lfm_sample_fixed")) return 1;
     if (method < LFM_METHOD_EULER || method > LFM_METHOD_RK4) return fail(ctx, "lfm_sample_fixed: unknown method %d", method);
@@ -1050,14 +1052,17 @@ extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const 
         const float third = (float)(1.0 / 3.0), two_thirds = (float)(2.0 / 3.0);
         for (int i = 0; i < n_int; ++i) {
             const float t0 = tg[i], t1 = tg[i + 1], dt = t1 - t0;
+            // options["perturb"]: the first evaluation of a step one ulp past t0 (Perturb.NEXT), rk4's last one ulp before
+            // t1 (Perturb.PREV) - in torchdiffeq's negated time; here in model time the directions flip
+            const float t0e = perturb ? nextafterf(t0, t0 - 1.0f) : t0;
             if (S == 2) {
-                ts[2 * i] = t0;
+                ts[2 * i] = t0e;
                 ts[2 * i + 1] = t0 + 0.5f * dt;
             } else {
-                ts[4 * i] = t0;
+                ts[4 * i] = t0e;
                 ts[4 * i + 1] = t0 + dt * third;
                 ts[4 * i + 2] = t0 + dt * two_thirds;
-                ts[4 * i + 3] = t1;
+                ts[4 * i + 3] = perturb ? nextafterf(t1, t1 + 1.0f) : t1;
             }
         }
         CUDA_OK(cudaMemcpyAsync(ctx->t_grid, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -1123,7 +1128,7 @@ extern "C" int lfm_sample_fixed(lfm_ctx* ctx, int method, float* x_inout, const 
     CUDA_OK(cudaMemcpyAsync(ctx->t_grid, t_grid_host, (size_t)n_grid * sizeof(float), cudaMemcpyDefault, s));
     CUDA_OK(cudaMemcpyAsync(ctx->x_state, x_inout, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (has_y) CUDA_OK(cudaMemcpyAsync(ctx->y_buf, y, (size_t)rows * sizeof(long long), cudaMemcpyDefault, s));
-    StepState st0{0, n_int};
+    StepState st0{0, n_int, perturb};
     CUDA_OK(cudaMemcpyAsync(ctx->step_state, &st0, sizeof(st0), cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaStreamSynchronize(s));  // st0 / t_grid_host are host stack/pageable memory
     int64_t nfe = 0;
@@ -1166,6 +1171,60 @@ static const double DP_MID[7] = {6025192743.0 / 30085553152.0 / 2, 0, 5125229292
                                  -2691868925.0 / 45128329728.0 / 2, 187940372067.0 / 1594534317056.0 / 2,
                                  -1776094331.0 / 19743644256.0 / 2, 11237099.0 / 235043384.0 / 2};
 
+// torchdiffeq's adaptive Runge-Kutta pairs (rk_common.RKAdaptiveStepsizeODESolver; SURVEY.md 8(c), oracle/solvers.py
+// _TABLEAUS): n = number of stage evaluations per step (alpha entries), k_1 = f0 and k_{n+1} = f1 of the next step.
+struct RkTableau {
+    int n, order;
+    double alpha[6], beta[6][6], c_sol[7], c_err[7], c_mid[7];
+    bool fsal;  // y1 == the last stage's input (c_sol[:n] == beta[n-1], c_sol[n] == 0)
+};
+static RkTableau make_tableau(int method) {
+    RkTableau t{};
+    if (method == LFM_ADAPTIVE_DOPRI5) {
+        t.n = 6;
+        t.order = 5;
+        t.fsal = true;
+        for (int i = 0; i < 6; ++i) {
+            t.alpha[i] = DP_ALPHA[i];
+            for (int j = 0; j < 6; ++j) t.beta[i][j] = DP_BETA[i][j];
+        }
+        for (int j = 0; j < 6; ++j) t.c_sol[j] = DP_BETA[5][j];
+        for (int j = 0; j < 7; ++j) {
+            t.c_err[j] = DP_CERR[j];
+            t.c_mid[j] = DP_MID[j];
+        }
+    } else if (method == LFM_ADAPTIVE_BOSH3) {  // Bogacki-Shampine 3(2)
+        t.n = 3;
+        t.order = 3;
+        t.fsal = true;
+        const double a[3] = {1.0 / 2, 3.0 / 4, 1.0};
+        const double b[3][3] = {{1.0 / 2, 0, 0}, {0.0, 3.0 / 4, 0}, {2.0 / 9, 1.0 / 3, 4.0 / 9}};
+        const double cs[4] = {2.0 / 9, 1.0 / 3, 4.0 / 9, 0.0};
+        const double ce[4] = {2.0 / 9 - 7.0 / 24, 1.0 / 3 - 1.0 / 4, 4.0 / 9 - 1.0 / 3, -1.0 / 8};
+        const double cm[4] = {0.0, 0.5, 0.0, 0.0};
+        for (int i = 0; i < 3; ++i) {
+            t.alpha[i] = a[i];
+            for (int j = 0; j < 3; ++j) t.beta[i][j] = b[i][j];
+        }
+        for (int j = 0; j < 4; ++j) {
+            t.c_sol[j] = cs[j];
+            t.c_err[j] = ce[j];
+            t.c_mid[j] = cm[j];
+        }
+    } else {  // LFM_ADAPTIVE_HEUN: Heun-Euler 2(1)
+        t.n = 1;
+        t.order = 2;
+        t.fsal = false;
+        t.alpha[0] = 1.0;
+        t.beta[0][0] = 1.0;
+        t.c_sol[0] = t.c_sol[1] = 0.5;
+        t.c_err[0] = 0.5;
+        t.c_err[1] = -0.5;
+        t.c_mid[0] = 0.5;
+    }
+    return t;
+}
+
 struct Dopri {
     lfm_ctx* ctx;
     cudaStream_t s;
@@ -1174,6 +1233,8 @@ struct Dopri {
     float cfg_scale;
     size_t n;
     int64_t nfe = 0;
+    RkTableau tab{};
+    int method = 0;
 };
 
 // k_out = -v(t = -s_time, y)   (model sees a 0-d fp32 time)
@@ -1221,12 +1282,17 @@ static int dp_record_step(Dopri& d, float atol, float rtol) {
     float* y0 = ctx->x_state;
     float* y1 = ctx->x_pred;
     float* ytmp = ctx->y_stage;
-    for (int i = 0; i < 6; ++i) {
-        float* yi = (i == 5) ? y1 : ytmp;
+    const int ns = d.tab.n;
+    for (int i = 0; i < ns; ++i) {
+        float* yi = (i == ns - 1 && d.tab.fsal) ? y1 : ytmp;
         rk_combine_dev_kernel<<<blocks_for(n), 256, 0, s>>>(y0, kp, i + 1, ctx->dp_dev->coef[i], yi, n);
         LAUNCH_OK();
         if (eval_velocity(ctx, s, ctx->dp_dev->t + i, 1, yi, d.n_img, d.y, d.cfg_scale, ctx->kbuf[i + 1])) return 1;
         negate_kernel<<<blocks_for(n), 256, 0, s>>>(ctx->kbuf[i + 1], n);
+        LAUNCH_OK();
+    }
+    if (!d.tab.fsal) {  // y1 = y0 + dt * sum_j c_sol[j] k_j  (coefficient row ns of the step block)
+        rk_combine_dev_kernel<<<blocks_for(n), 256, 0, s>>>(y0, kp, ns + 1, ctx->dp_dev->coef[ns], y1, n);
         LAUNCH_OK();
     }
     rms_ratio_partial_kernel<<<kRmsBlocks, 256, 0, s>>>(nullptr, nullptr, kp, RkCoef{}, y0, y1, atol, rtol, n, ctx->partial,
@@ -1241,8 +1307,8 @@ static int dp_record_step(Dopri& d, float atol, float rtol) {
 static int dp_get_graph(Dopri& d, float atol, float rtol, cudaGraphExec_t* out, int* launches) {
     lfm_ctx* ctx = d.ctx;
     char key[160];
-    snprintf(key, sizeof(key), "dp_n%d_y%d_c%.6f_a%.9g_r%.9g", d.n_img, d.y != nullptr ? 1 : 0, d.cfg_scale > 1.0f ? d.cfg_scale : 0.f,
-             atol, rtol);
+    snprintf(key, sizeof(key), "dp%d_n%d_y%d_c%.6f_a%.9g_r%.9g", d.method, d.n_img, d.y != nullptr ? 1 : 0,
+             d.cfg_scale > 1.0f ? d.cfg_scale : 0.f, atol, rtol);
     auto it = ctx->graphs.find(key);
     if (it != ctx->graphs.end()) {
         *out = it->second.exec;
@@ -1276,16 +1342,26 @@ static int dp_get_graph(Dopri& d, float atol, float rtol, cudaGraphExec_t* out, 
 
 extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double t1, double rtol, double atol,
                                  const int64_t* y, int B_img, float cfg_scale, lfm_ode_stats* stats, void* stream) {
+    return lfm_sample_adaptive(ctx, LFM_ADAPTIVE_DOPRI5, x_inout, t0, t1, rtol, atol, y, B_img, cfg_scale, stats, stream);
+}
+
+extern "C" int lfm_sample_adaptive(lfm_ctx* ctx, int method, float* x_inout, double t0, double t1, double rtol, double atol,
+                                   const int64_t* y, int B_img, float cfg_scale, lfm_ode_stats* stats, void* stream) {
     const int rows = cfg_scale > 1.0f ? 2 * B_img : B_img;
-    if (check_ready(ctx, rows, "lfm_sample_dopri5")) return 1;
-    if (x_inout == nullptr) return fail(ctx, "lfm_sample_dopri5: null tensor");
-    if (!(t0 > t1)) return fail(ctx, "lfm_sample_dopri5: expects t0 > t1 (reference integrates t: 1 -> 0)");
-    if (cfg_scale > 1.0f && y == nullptr) return fail(ctx, "lfm_sample_dopri5: CFG needs labels");
+    if (check_ready(ctx, rows, "lfm_sample_adaptive")) return 1;
+    if (method < LFM_ADAPTIVE_DOPRI5 || method > LFM_ADAPTIVE_HEUN) return fail(ctx, "lfm_sample_adaptive: unknown method %d", method);
+    if (x_inout == nullptr) return fail(ctx, "lfm_sample_adaptive: null tensor");
+    if (!(t0 > t1)) return fail(ctx, "lfm_sample_adaptive: expects t0 > t1 (reference integrates t: 1 -> 0)");
+    if (cfg_scale > 1.0f && y == nullptr) return fail(ctx, "lfm_sample_adaptive: CFG needs labels");
     CUDA_OK(cudaSetDevice(ctx->device));
     g_num_sms = ctx->num_sms;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     if (join_in(ctx, user)) return 1;
     Dopri d{ctx, ctx->stream, B_img, nullptr, cfg_scale, (size_t)B_img * ctx->chw};
+    d.tab = make_tableau(method);
+    d.method = method;
+    const RkTableau& tab = d.tab;
+    const int ns = tab.n;
     cudaStream_t s = d.s;
     const size_t n = d.n;
     if (y != nullptr) {
@@ -1309,7 +1385,7 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
     CUDA_OK(cudaMemcpyAsync(y0, x_inout, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     double s0 = -t0;
     const double s_end = -t1;
-    // _before_integrate: f0 and the initial step (order 4 rule); two synchronisations
+    // _before_integrate: f0 and the initial step (_select_initial_step with order - 1); two synchronisations
     if (dp_func(d, (float)s0, y0, k[0])) return 1;
     if (dp_rms_launch(d, y0, nullptr, y0, atol_f, rtol_f, 0)) return 1;
     if (dp_rms_launch(d, k[0], nullptr, y0, atol_f, rtol_f, 1)) return 1;
@@ -1327,24 +1403,26 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
     if (d1 <= 1e-15f && d2 <= 1e-15f)
         h1 = fmaxf(1e-6f, h0 * 1e-3f);
     else
-        h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / 5.0f);
+        h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / (float)tab.order);
     double dt = (double)fminf(100.f * h0, fabsf(h1));
 
     double s_hi = s0;
     int64_t accepted = 0, rejected = 0;
     bool have_interp = false;
     while (s_end > s_hi) {
-        if (accepted + rejected > 100000) return fail(ctx, "lfm_sample_dopri5: step limit exceeded");
+        if (accepted + rejected > 100000) return fail(ctx, "lfm_sample_adaptive: step limit exceeded");
         const double t0s = s_hi, t1s = t0s + dt;
         const float t0_32 = (float)t0s, dt_32 = (float)dt, t1_32 = (float)t1s;
         DpStep* hp = ctx->dp_host;  // the previous step's upload has completed: every step ends with a synchronisation
         memset(hp, 0, sizeof(DpStep));
-        for (int i = 0; i < 6; ++i) {
-            for (int j = 0; j <= i; ++j) hp->coef[i][j] = (float)DP_BETA[i][j] * dt_32;
-            const float si = DP_ALPHA[i] == 1.0 ? nextafterf(t1_32, t1_32 - 1.0f) : t0_32 + (float)DP_ALPHA[i] * dt_32;
+        for (int i = 0; i < ns; ++i) {
+            for (int j = 0; j <= i; ++j) hp->coef[i][j] = (float)tab.beta[i][j] * dt_32;
+            const float si = tab.alpha[i] == 1.0 ? nextafterf(t1_32, t1_32 - 1.0f) : t0_32 + (float)tab.alpha[i] * dt_32;
             hp->t[i] = -si;
         }
-        for (int j = 0; j < 7; ++j) hp->cerr[j] = dt_32 * (float)DP_CERR[j];
+        if (!tab.fsal)
+            for (int j = 0; j <= ns; ++j) hp->coef[ns][j] = (float)tab.c_sol[j] * dt_32;
+        for (int j = 0; j <= ns; ++j) hp->cerr[j] = dt_32 * (float)tab.c_err[j];
         CUDA_OK(cudaMemcpyAsync(ctx->dp_dev, hp, sizeof(DpStep), cudaMemcpyHostToDevice, s));
         if (g_step != nullptr) {
             CUDA_OK(cudaGraphLaunch(g_step, s));
@@ -1353,7 +1431,7 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
             return 1;
         }
         CUDA_OK(cudaStreamSynchronize(s));  // the ONE synchronisation of the step: the controller runs on the host in fp64
-        d.nfe += 6;
+        d.nfe += ns;
         const float ratio = fabsf(ctx->ratio_host[0]);
         const bool accept = ratio <= 1.0f;
         if (accept) {
@@ -1362,14 +1440,16 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
             if (t1s >= s_end) {
                 // last step: evaluate the quartic dense output at s_end and finish
                 RkCoef cm{};
-                for (int j = 0; j < 7; ++j) cm.c[j] = dt_32 * (float)DP_MID[j];
+                for (int j = 0; j <= ns; ++j) cm.c[j] = dt_32 * (float)tab.c_mid[j];
                 const float xq = (float)((s_end - t0s) / (t1s - t0s));
-                dopri_interp_kernel<<<blocks_for(n), 256, 0, s>>>(y0, y1, kp, cm, dt_32, xq, ytmp, n);
+                RkPtrs kq = kp;
+                kq.k[6] = k[ns];  // the interpolant's f1 is the LAST stage derivative (slot 6 of the kernel's argument)
+                dopri_interp_kernel<<<blocks_for(n), 256, 0, s>>>(y0, y1, kq, cm, dt_32, xq, ytmp, n);
                 LAUNCH_OK();
                 have_interp = true;
                 break;
             }
-            dp_accept_kernel<<<blocks_for(n), 256, 0, s>>>(y0, y1, k[0], k[6], n);  // y0 <- y1, f0 <- k7 (FSAL)
+            dp_accept_kernel<<<blocks_for(n), 256, 0, s>>>(y0, y1, k[0], k[ns], n);  // y0 <- y1, f0 <- the last stage derivative
             LAUNCH_OK();
         } else {
             rejected++;
@@ -1379,11 +1459,11 @@ extern "C" int lfm_sample_dopri5(lfm_ctx* ctx, float* x_inout, double t0, double
             factor = 10.0;
         } else {
             const double dfactor = ratio < 1.f ? 1.0 : 0.2;
-            factor = fmin(10.0, fmax(0.9 / pow((double)ratio, 1.0 / 5.0), dfactor));
+            factor = fmin(10.0, fmax(0.9 / pow((double)ratio, 1.0 / (double)tab.order), dfactor));
         }
         dt = dt * factor;
     }
-    if (!have_interp) return fail(ctx, "lfm_sample_dopri5: integration produced no step");
+    if (!have_interp) return fail(ctx, "lfm_sample_adaptive: integration produced no step");
     CUDA_OK(cudaMemcpyAsync(x_inout, ytmp, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (join_out(ctx, user)) return 1;
     if (stats != nullptr) {

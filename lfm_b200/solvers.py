@@ -109,17 +109,11 @@ def sample_from_model(model, x_0, model_kwargs, args):
     else:
         mk.pop("cfg_scale", None)
     x, y, cfg_scale, doubled = _split_cfg(x_0, mk)
-    if method == "euler":
-        if getattr(args, "perturb", False):
-            raise NotImplementedError("perturb=True is not implemented natively")
+    if method in ("euler", "midpoint", "rk4"):
+        flags = 2 if getattr(args, "perturb", False) else 0        # LFM_FIXED_PERTURB (test_flow_latent.py:44-48,64)
         nodes = euler_time_grid(float(args.step_size))
-        xf, stats = _run_fixed(model, x, y, cfg_scale, nodes, "euler", 0, 0)
-    elif method in ("midpoint", "rk4"):
-        if getattr(args, "perturb", False):
-            raise NotImplementedError("perturb=True is not implemented natively")
-        nodes = euler_time_grid(float(args.step_size))
-        xf, stats = _run_fixed(model, x, y, cfg_scale, nodes, method, 0, 0)
-    elif method == "dopri5":
+        xf, stats = _run_fixed(model, x, y, cfg_scale, nodes, method, flags, 0)
+    elif method in ("dopri5", "bosh3", "adaptive_heun"):
         net = _unwrap(model)
         xf = x.to(torch.float32).contiguous().clone()
         n_img = xf.shape[0]
@@ -127,13 +121,14 @@ def sample_from_model(model, x_0, model_kwargs, args):
         y = _check_labels(net, y, rows, xf.device)
         ctx = net.native(rows, xf.device)
         st = _lib.OdeStats()
-        _lib.check(_lib.load().lfm_sample_dopri5(ctx, xf.data_ptr(), 1.0, 0.0, float(args.rtol), float(args.atol),
-                                                 y.data_ptr() if y is not None else None, n_img, float(cfg_scale),
-                                                 C.byref(st), _NativeNet._stream(xf.device)), ctx)
+        _lib.check(_lib.load().lfm_sample_adaptive(ctx, {"dopri5": 0, "bosh3": 1, "adaptive_heun": 2}[method], xf.data_ptr(), 1.0, 0.0,
+                                                   float(args.rtol), float(args.atol), y.data_ptr() if y is not None else None,
+                                                   n_img, float(cfg_scale), C.byref(st), _NativeNet._stream(xf.device)), ctx)
         stats = dict(nfe=int(st.nfe), accepted=int(st.accepted), rejected=int(st.rejected))
         net.last_stats = stats
     else:
-        raise NotImplementedError(f"method '{method}' has no native implementation (euler, midpoint, rk4 and dopri5 do)")
+        raise NotImplementedError(f"method '{method}' has no native implementation (euler, midpoint, rk4, dopri5, bosh3 and "
+                                  "adaptive_heun do)")
     if doubled:
         xf = torch.cat([xf, xf], 0)
     traj = torch.stack([x_0.to(xf.dtype), xf], 0)

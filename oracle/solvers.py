@@ -87,7 +87,7 @@ def tdq_euler_grid(step_size: float, t0: float = 1.0, t1: float = 0.0) -> torch.
 
 
 @torch.no_grad()
-def tdq_euler(f, x0, step_size: float, t0: float = 1.0, t1: float = 0.0):
+def tdq_euler(f, x0, step_size: float, t0: float = 1.0, t1: float = 0.0, perturb: bool = False):
     """``odeint(f, x0, [t0, t1], method='euler', options=dict(step_size=h))[-1]``.
 
     In negated time the wrapped field is ``-f(-s, y)`` and ``y += (s_{k+1} - s_k) * (-f)``; the
@@ -99,12 +99,14 @@ def tdq_euler(f, x0, step_size: float, t0: float = 1.0, t1: float = 0.0):
     y = x0
     for k in range(len(tk) - 1):
         dt = sk[k + 1] - sk[k]
-        y = y + dt * (-f(tk[k], y))
+        # options["perturb"]: Perturb.NEXT on the step's evaluation = nextafter(s_k, s_k + 1) in negated time
+        tm = -torch.nextafter(sk[k], sk[k] + 1) if perturb else tk[k]
+        y = y + dt * (-f(tm, y))
     return y, len(tk) - 1
 
 
 @torch.no_grad()
-def tdq_fixed_rk(f, x0, step_size: float, method: str, t0: float = 1.0, t1: float = 0.0):
+def tdq_fixed_rk(f, x0, step_size: float, method: str, t0: float = 1.0, t1: float = 0.0, perturb: bool = False):
     """torchdiffeq fixed-grid ``midpoint`` / ``rk4`` (v0.2.3 fixed_grid.py; ``rk4`` is the 3/8-rule
     ``rk4_alt_step_func``) on the same grid as :func:`tdq_euler`.  Integrates s = -t with the field -f(-s, y);
     stage times and dt are fp32 tensors, ``_one_third`` / ``_two_thirds`` python floats.  Returns (x_final, nfe)."""
@@ -121,16 +123,18 @@ def tdq_fixed_rk(f, x0, step_size: float, method: str, t0: float = 1.0, t1: floa
     for k in range(len(tk) - 1):
         s0, s1 = sk[k], sk[k + 1]
         dt = s1 - s0
+        s0e = torch.nextafter(s0, s0 + 1) if perturb else s0      # Perturb.NEXT on the first evaluation of the step
+        s1e = torch.nextafter(s1, s1 - 1) if perturb else s1      # Perturb.PREV on rk4's last evaluation
         if method == "midpoint":
             half_dt = 0.5 * dt
-            f0 = ft(s0, y)
+            f0 = ft(s0e, y)
             y_mid = y + f0 * half_dt
             y = y + dt * ft(s0 + half_dt, y_mid)
         elif method == "rk4":
-            k1 = ft(s0, y)
+            k1 = ft(s0e, y)
             k2 = ft(s0 + dt * one_third, y + dt * k1 * one_third)
             k3 = ft(s0 + dt * two_thirds, y + dt * (k2 - k1 * one_third))
-            k4 = ft(s1, y + dt * (k1 - k2 + k3))
+            k4 = ft(s1e, y + dt * (k1 - k2 + k3))
             y = y + (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
         else:
             raise KeyError(method)
@@ -171,15 +175,37 @@ class Dopri5Stats:
         self.rejected = 0
 
 
-@torch.no_grad()
+# torchdiffeq's other Runge-Kutta pairs that the reference CLI accepts (test_flow_latent.py:27 ADAPTIVE_SOLVER; the same
+# rk_common.RKAdaptiveStepsizeODESolver with another tableau).  Restated from memory of torchdiffeq 0.2.3 (bosh3.py,
+# adaptive_heun.py); UNPINNED like dopri5, anchored on tableau identities and scipy's RK23 (= Bogacki-Shampine).
+_TABLEAUS = {
+    "dopri5": dict(order=5, alpha=_DP_ALPHA, beta=_DP_BETA, c_sol=_DP_CSOL, c_err=_DP_CERR, c_mid=_DP_MID),
+    "bosh3": dict(order=3, alpha=[1 / 2, 3 / 4, 1.0], beta=[[1 / 2], [0.0, 3 / 4], [2 / 9, 1 / 3, 4 / 9]],
+                  c_sol=[2 / 9, 1 / 3, 4 / 9, 0.0], c_err=[2 / 9 - 7 / 24, 1 / 3 - 1 / 4, 4 / 9 - 1 / 3, -1 / 8],
+                  c_mid=[0.0, 0.5, 0.0, 0.0]),
+    "adaptive_heun": dict(order=2, alpha=[1.0], beta=[[1.0]], c_sol=[0.5, 0.5], c_err=[0.5, -0.5], c_mid=[0.5, 0.0]),
+}
+
+
 def tdq_dopri5(f, x0, rtol=1e-5, atol=1e-5, t0: float = 1.0, t1: float = 0.0, max_steps=100000):
-    """``odeint(f, x0, [t0, t1], method='dopri5', rtol, atol, options=dict(dtype=float64))[-1]``.
+    return tdq_adaptive(f, x0, "dopri5", rtol, atol, t0, t1, max_steps)
+
+
+@torch.no_grad()
+def tdq_adaptive(f, x0, method="dopri5", rtol=1e-5, atol=1e-5, t0: float = 1.0, t1: float = 0.0, max_steps=100000):
+    """``odeint(f, x0, [t0, t1], method=method, rtol, atol, options=dict(dtype=float64))[-1]`` for the Runge-Kutta pairs of
+    ``_TABLEAUS`` (rk_common.RKAdaptiveStepsizeODESolver).
 
     State y in fp32; time, dt and the controller in fp64; stage times/dt are cast to fp32 inside the
     Runge-Kutta step; the model sees a 0-d fp32 t; stages with alpha == 1 are evaluated one fp32
     ulp before the step end (``Perturb.PREV``).  The error norm is the RMS over the whole batch
-    tensor, so the step sequence depends on the batch.  Returns (x_final, Dopri5Stats).
+    tensor, so the step sequence depends on the batch.  ``_select_initial_step`` runs with ``order - 1``, the step
+    controller with ``order``; ``y1`` is the last stage's input when the tableau is first-same-as-last, else
+    ``y0 + dt * sum c_sol k``; ``f1`` is ALWAYS the last stage derivative.  Returns (x_final, Dopri5Stats).
     """
+    tab = _TABLEAUS[method]
+    order = tab["order"]
+    nst = len(tab["alpha"])
     st = Dopri5Stats()
     f32, f64 = torch.float32, torch.float64
 
@@ -197,7 +223,7 @@ def tdq_dopri5(f, x0, rtol=1e-5, atol=1e-5, t0: float = 1.0, t1: float = 0.0, ma
     s_end = torch.tensor(-t1, dtype=f64)
     y0 = x0.to(f32)
 
-    # _before_integrate + _select_initial_step(order = 4)
+    # _before_integrate + _select_initial_step(order - 1)
     f0 = func(s0, y0)
     scale = (atol_t + y0.abs() * rtol_t).to(f32)
     d0 = _rms(y0 / scale)
@@ -212,13 +238,15 @@ def tdq_dopri5(f, x0, rtol=1e-5, atol=1e-5, t0: float = 1.0, t1: float = 0.0, ma
     if d1 <= 1e-15 and d2 <= 1e-15:
         h1 = torch.max(torch.tensor(1e-6, dtype=f32), h0 * 1e-3)
     else:
-        h1 = (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+        h1 = (0.01 / max(d1, d2)) ** (1.0 / float(order))
     dt = torch.min(100 * h0, h1.abs()).to(f64)
 
-    alpha = torch.tensor(_DP_ALPHA, dtype=f32)
-    beta = [torch.tensor(b, dtype=f32) for b in _DP_BETA]
-    c_err = torch.tensor(_DP_CERR, dtype=f32)
-    c_mid = torch.tensor(_DP_MID, dtype=f32)
+    alpha = torch.tensor(tab["alpha"], dtype=f32)
+    beta = [torch.tensor(b, dtype=f32) for b in tab["beta"]]
+    c_sol = torch.tensor(tab["c_sol"], dtype=f32)
+    c_err = torch.tensor(tab["c_err"], dtype=f32)
+    c_mid = torch.tensor(tab["c_mid"], dtype=f32)
+    fsal = float(c_sol[-1]) == 0.0 and bool((c_sol[:-1] == beta[-1]).all())
 
     s_lo = s0           # rk_state.t0 of the last accepted step
     s_hi = s0           # rk_state.t1
@@ -232,7 +260,7 @@ def tdq_dopri5(f, x0, rtol=1e-5, atol=1e-5, t0: float = 1.0, t1: float = 0.0, ma
         t0_32, dt_32, t1_32 = t0s.to(f32), dt.to(f32), t1s.to(f32)
         k = [f0]
         yi = y0
-        for i in range(6):
+        for i in range(nst):
             if float(alpha[i]) == 1.0:
                 ti, perturb = t1_32, -1
             else:
@@ -240,6 +268,8 @@ def tdq_dopri5(f, x0, rtol=1e-5, atol=1e-5, t0: float = 1.0, t1: float = 0.0, ma
             yi = y0 + torch.stack(k, dim=-1).matmul(beta[i] * dt_32).view_as(f0)
             k.append(func(ti, yi, perturb))
         K = torch.stack(k, dim=-1)
+        if not fsal:
+            yi = y0 + K.matmul(dt_32 * c_sol).view_as(f0)
         y1, f1 = yi, k[-1]
         err = K.matmul(dt_32 * c_err)
         tol = (atol_t + rtol_t * torch.max(y0.abs(), y1.abs())).to(f32)
@@ -257,13 +287,13 @@ def tdq_dopri5(f, x0, rtol=1e-5, atol=1e-5, t0: float = 1.0, t1: float = 0.0, ma
             y0, f0 = y1, f1
         else:
             st.rejected += 1
-        # _optimal_step_size(order = 5)
+        # _optimal_step_size(order)
         if ratio == 0:
             dt = dt * 10.0
         else:
             r = ratio.to(f64)
             dfactor = 1.0 if ratio < 1 else 0.2
-            factor = min(10.0, max(0.9 / float(r) ** (1.0 / 5.0), dfactor))
+            factor = min(10.0, max(0.9 / float(r) ** (1.0 / float(order)), dfactor))
             dt = dt * factor
     # _interp_evaluate at s_end inside the last accepted step
     xq = ((s_end - s_lo) / (s_hi - s_lo)).to(f32)

@@ -227,8 +227,26 @@ def test_torchdiffeq_euler_and_dopri5_vs_oracle(dev):
         ref, n = osol.tdq_fixed_rk(f, x, 0.2, m)
         assert int(nfe) == n == 5 * per
         assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
+    # options["perturb"] (--perturb, test_flow_latent.py:44-48,64): first evaluation of a step one ulp past the node
+    for m in ("euler", "rk4"):
+        args = types.SimpleNamespace(method=m, step_size=0.2, perturb=True, cfg_scale=1.0, compute_nfe=False)
+        traj = lfm_b200.sample_from_model(net, x.to(dev), {}, args)
+        ref = (osol.tdq_euler(f, x, 0.2, perturb=True) if m == "euler" else osol.tdq_fixed_rk(f, x, 0.2, m, perturb=True))[0]
+        assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
+    # the other adaptive pairs of torchdiffeq the CLI accepts (test_flow_latent.py:27): same controller, other tableau
+    for m, per in (("bosh3", 3), ("adaptive_heun", 1)):
+        args = types.SimpleNamespace(method=m, atol=1e-2, rtol=1e-2, cfg_scale=1.0, compute_nfe=True)
+        traj, nfe = lfm_b200.sample_from_model(net, x.to(dev), {}, args)
+        ref, st = osol.tdq_adaptive(f, x, m, rtol=1e-2, atol=1e-2)
+        s = net.last_stats
+        assert (s["nfe"], s["accepted"], s["rejected"]) == (st.nfe, st.accepted, st.rejected) and int(nfe) == 2 + per * (st.accepted + st.rejected)
+        assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E
+        args = types.SimpleNamespace(method=m, atol=1e-3, rtol=1e-3, cfg_scale=1.0, compute_nfe=False)
+        traj = lfm_b200.sample_from_model(net, x.to(dev), {}, args)
+        ref, st = osol.tdq_adaptive(f, x, m, rtol=1e-3, atol=1e-3)
+        assert rel_l2(traj[-1].cpu(), ref) < TOL_E2E and abs(net.last_stats["nfe"] - st.nfe) <= 6 * per
     with pytest.raises(NotImplementedError):
-        lfm_b200.sample_from_model(net, x.to(dev), {}, types.SimpleNamespace(method="bosh3", step_size=0.1, cfg_scale=1.0))
+        lfm_b200.sample_from_model(net, x.to(dev), {}, types.SimpleNamespace(method="dopri8", step_size=0.1, cfg_scale=1.0, atol=1e-3, rtol=1e-3))
 
 
 def test_dopri5_with_cfg_vs_oracle(dev):

@@ -159,3 +159,24 @@ def test_tdq_fixtures_from_real_torchdiffeq(name):
         out, st = osol.tdq_dopri5(f, x0, rtol=tol, atol=tol)
         assert st.nfe == int(z[key + "_nfe"])                                                # same accept/reject sequence
         assert rel_l2(out, z[key]) < 1e-5
+
+
+def test_other_adaptive_pairs_known_answers():
+    """bosh3 / adaptive_heun restatements (torchdiffeq bosh3.py / adaptive_heun.py from memory; unpinned): tableau identities,
+    NFE = 2 + stages * steps, convergence on dx/dt = -x, and the Bogacki-Shampine weights against scipy's RK23 tableau."""
+    from scipy.integrate import RK23
+    tb = osol._TABLEAUS["bosh3"]
+    assert np.allclose(tb["c_sol"][:3], RK23.B) and np.allclose(tb["alpha"][:2], RK23.C[1:]) and np.allclose(-RK23.E, tb["c_err"])      # scipy stores low - high
+    for name, stages in (("bosh3", 3), ("adaptive_heun", 1), ("dopri5", 6)):
+        t = osol._TABLEAUS[name]
+        assert abs(sum(t["c_sol"]) - 1) < 1e-12 and abs(sum(t["c_err"])) < 1e-12 and len(t["alpha"]) == stages
+        for a, b in zip(t["alpha"], t["beta"]):
+            assert abs(sum(b) - a) < 1e-12
+        x0 = torch.tensor([[1.0, -2.0, 0.5]])
+        errs = []
+        for tol in (1e-3, 1e-5):
+            out, st = osol.tdq_adaptive(lambda tt, xx: -xx, x0, name, tol, tol)
+            assert st.nfe == 2 + stages * (st.accepted + st.rejected)
+            errs.append(float((out / x0 - math.e).abs().max()))
+        assert errs[1] < errs[0] and errs[1] < 5e-3
+
