@@ -192,7 +192,7 @@ int64_t lfm_launch_count(const lfm_ctx* ctx);
 int lfm_dbg_gemm(const void* a_bf16, const void* w_bf16, const float* bias, void* out, const float* gate,
                  int gate_stride, int rows_per_sample, int M, int N, int K, int epi, int block_n, void* stream);
 /* softmax(q k^T / 8) v on a [B*256, 3*D] bf16 qkv buffer -> out [B*256, D] bf16.  variant: 3 = persistent single-TMEM-read kernel (default), 2 = persistent two-pass, 0 = P in TMEM,
- * 1 = P through shared memory, 5 = version 3 with one MMA issuer thread per query tile ("ping-pong", attention5.cuh).  dbg_s (optional) receives the raw S = q k^T as fp32 [B, H, 256, 256]. */
+ * 1 = P through shared memory.  dbg_s (optional) receives the raw S = q k^T as fp32 [B, H, 256, 256]. */
 int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, int H, int variant, float* dbg_s, void* stream);
 /* Intermediate activations of the last lfm_forward (fp32 token stream [B*T, D] after all blocks). */
 int lfm_dbg_tokens(lfm_ctx* ctx, float* out, int B);

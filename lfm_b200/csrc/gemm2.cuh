@@ -550,7 +550,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     continue;
                 }
                 epilogue_math<EPI>(va, f, ep, nbase + c * 32, N, gate_row, add_row);
-                if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + c * 32, N, lane);
+                if ((EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_BF16) && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + c * 32, N, lane);
                 // this staging tile is free once all but the most recent TMA op of this warp have READ their tile
                 uint8_t* stg = stg0 + sbuf * 4096;
                 if (kBf16Out && direct_bf16) {
@@ -584,7 +584,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 tmem_ld_wait();
                 if (c + 2 < nch) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
                 epilogue_math<EPI>(vb, f, ep, nbase + (c + 1) * 32, N, gate_row, add_row);
-                if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + (c + 1) * 32, N, lane);
+                if ((EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_BF16) && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + (c + 1) * 32, N, lane);
                 if (kBf16Out) {
                     stage_row_bf16_half(stg, lane, f, 1);
                     fence_proxy_async();

@@ -362,7 +362,7 @@ gemm5_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                         tmem_ld_wait();
                         tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
                         epilogue_math<EPI>(va, f, ep, nbase + c * 32, N, gate_row, add_row);
-                        if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + c * 32, N, lane);
+                        if ((EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_BF16) && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + c * 32, N, lane);
                         __syncwarp();  // the previous read-back of the staging tile is complete
                         if (kBf16Out) {
                             stage_row_bf16_half(stg, lane, f, 0);
@@ -375,7 +375,7 @@ gemm5_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                         tmem_ld_wait();
                         if (c + 2 < nch) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
                         epilogue_math<EPI>(vb, f, ep, nbase + (c + 1) * 32, N, gate_row, add_row);
-                        if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + (c + 1) * 32, N, lane);
+                        if ((EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_BF16) && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + (c + 1) * 32, N, lane);
                         if (kBf16Out) {
                             stage_row_bf16_half(stg, lane, f, 1);
                             __syncwarp();
@@ -400,7 +400,7 @@ gemm5_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     tmem_ld_wait();
                     tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
                     epilogue_math<EPI>(va, f, ep, nbase + c * 32, N, gate_row, add_row);
-                    if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + c * 32, N, lane);
+                    if ((EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_BF16) && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + c * 32, N, lane);
                     if (lane == 0) tma_store_wait_read<0>();
                     __syncwarp();
                     if (kBf16Out) {
@@ -422,7 +422,7 @@ gemm5_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                     tmem_ld_wait();
                     if (c + 2 < nch) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
                     epilogue_math<EPI>(vb, f, ep, nbase + (c + 1) * 32, N, gate_row, add_row);
-                    if (EPI == EPI_BIAS_F32 && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + (c + 1) * 32, N, lane);
+                    if ((EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_BF16) && ep.gn_bins != nullptr) gn_accumulate(f, ep, row, M, nbase + (c + 1) * 32, N, lane);
                     if (kBf16Out) {
                         stage_row_bf16_half(stg, lane, f, 1);
                         fence_proxy_async();

@@ -16,7 +16,6 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "attention3.cuh"
-#include "attention5.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -359,12 +358,6 @@ static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, con
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
-    if (variant == 5) {  // per-tile MMA issuers, staggered ("ping-pong") - attention5.cuh
-        static DevOnce once5;
-        static const int stagger = env_int("LFM_ATTN_STAGGER", 1);
-        if (cudaError_t e = smem_opt_in(once5, attention5_t256_d64, kA2SmemBytes)) return e;
-        return launch_k(attention5_t256_d64, dim3(grid), kA5Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse, stagger);
-    }
     if (variant == 3)
         return launch_k(attention3_t256_d64, dim3(grid), kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
     else

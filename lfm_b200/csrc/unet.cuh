@@ -85,6 +85,8 @@ gn_stats_kernel(Src2 s, int HW, int nchunk, double* __restrict__ partial) {
 // unet.py:238 `skip_connection(x) + h`) and/or writes a raw bf16 cast (operand of the 1x1 skip convolution).
 struct GnApplyArgs {
     Src2 src;
+    const __nv_bfloat16* src_bf16;  // nullptr, or the source as bf16 [B, HW, C] (conv1's output when its fp32 statistics were
+                                    // taken in that conv's epilogue: half the bytes to write and to read back)
     int HW, C, nchunk;
     const double* partial;
     const unsigned long long* bins;  // nullptr, or fixed-point {sum, sumsq} per (sample, group) from the producing conv
@@ -150,7 +152,16 @@ gn_apply_kernel(GnApplyArgs a) {
             float4 vv[JB];
 #pragma unroll
             for (int u = 0; u < JB; ++u)
-                if (j0 + u < J) vv[u] = src2_load(a.src, pix, 128 * (j0 + u) + 4 * lane);
+                if (j0 + u < J) {
+                    if (a.src_bf16 != nullptr) {
+                        const uint2 r = *reinterpret_cast<const uint2*>(a.src_bf16 + pix * C + 128 * (j0 + u) + 4 * lane);
+                        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+                        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+                        vv[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    } else {
+                        vv[u] = src2_load(a.src, pix, 128 * (j0 + u) + 4 * lane);
+                    }
+                }
 #pragma unroll
             for (int u = 0; u < JB; ++u) {
                 if (j0 + u < J) {

@@ -49,10 +49,33 @@ class _NativeNet(nn.Module):
         self._ctx_rows = 0
         self._ctx_device = None
         self._uploaded_version = None
+        self._dirty = True          # parameters may differ from the uploaded copy: do the full version walk
+        self._probe = None          # O(1) fingerprint (first / last parameter) checked on every call
         self.last_stats = None
 
     def _version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _quick_probe(self):
+        ps = self._probe_params
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
+    # everything that can change parameters through the nn.Module interface marks the native copy stale; direct in-place
+    # edits of a parameter tensor are caught by the O(1) probe when they touch the first / last parameter, otherwise
+    # call mark_dirty().  (Round 1 walked all 252-428 tensors on every model(t, x) call: ~100 us per NFE for callers that
+    # drive the solver from Python, e.g. the reference's own odeint or --measure_time.)
+    def mark_dirty(self):
+        self._dirty = True
+
+    def _apply(self, fn, *a, **k):
+        self._dirty = True
+        object.__setattr__(self, "_probe_cache", None)   # .to() / .to_empty() may replace the Parameter objects
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._dirty = True
+        object.__setattr__(self, "_probe_cache", None)
+        return super().load_state_dict(*a, **k)
 
     def _release(self):
         if getattr(self, "_ctx", None) is not None:
@@ -75,9 +98,14 @@ class _NativeNet(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("lfm_b200 runs on a CUDA device (B200, sm_100a) only; got tensors on " + str(device))
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        if (self._ctx is not None and not self._dirty and rows <= self._ctx_rows and self._ctx_device == dev_index
+                and self._quick_probe() == self._probe):
+            return self._ctx                     # fast path: nothing changed since the upload
         ver = self._version()
         if (self._ctx is not None and rows <= self._ctx_rows and self._ctx_device == dev_index
                 and ver == self._uploaded_version):
+            self._dirty = False
+            self._probe = self._quick_probe()
             return self._ctx
         self._release()
         ctx = self._create_ctx(lib, dev_index)
@@ -92,7 +120,18 @@ class _NativeNet(nn.Module):
             lib.lfm_destroy(ctx)
             raise
         self._ctx, self._ctx_rows, self._ctx_device, self._uploaded_version = ctx, max_rows, dev_index, ver
+        self._dirty = False
+        self._probe = self._quick_probe()
         return ctx
+
+    @property
+    def _probe_params(self):
+        ps = getattr(self, "_probe_cache", None)
+        if ps is None:
+            allp = list(self.parameters())
+            ps = (allp[0], allp[-1]) if allp else ()
+            object.__setattr__(self, "_probe_cache", ps)
+        return ps
 
     @staticmethod
     def _stream(device):

@@ -159,6 +159,7 @@ class AutoencoderKL(_NativeNet):
             raise ValueError(f"expected square latents [B, {self.latent_channels}, s, s], got {tuple(z.shape)}")
         if self._latent_size != h:
             self._latent_size = h
+            self._dirty = True              # another latent size = another native context
         up = 2 ** (len(self.block_out_channels) - 1)
         out = torch.empty(B, self.out_channels, h * up, w * up, device=z.device) if want_f32 else None
         u8 = torch.empty(B, h * up, w * up, self.out_channels, device=z.device, dtype=torch.uint8) if want_u8 else None

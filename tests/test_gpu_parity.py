@@ -99,7 +99,7 @@ def test_gemm_epilogues(dev, M, N, K, epi, bn):
     assert rel_l2(out.float().cpu(), ref.cpu()) < tol
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("B,H", [(1, 1), (2, 4), (3, 12), (64, 16)])
 def test_attention(dev, variant, B, H):
     lib = _lib.load()
