@@ -50,7 +50,14 @@ struct GemmEpi {
     // epilogue, which a reduce-add performed at L2 never sees.
     const float* addend = nullptr;
     int dbg_flags = 0;  // measurement aids (LFM_G2_DBG): 1 = the epilogue releases the accumulator without draining it
+    // Completed blocks are published in a GLOBAL queue and every CTA's finisher warps pull 4-row units from it (ticket
+    // counter): the LayerNorm work is spread over the whole chip instead of landing on whichever CTA arrived last (round 2's
+    // first version: 2.6x slower end to end).  fin_ctl: two control blocks of fin_stride ints {ticket, tail, -, -,
+    // queue[m_blocks]}; a launch uses block fin_set and re-initialises the OTHER one for the finisher launch after it.
     int* rb_count = nullptr;
+    int* fin_ctl = nullptr;
+    int fin_stride = 0;
+    int fin_set = 0;
     __nv_bfloat16* ln_out = nullptr;
     const float* ln_shift = nullptr;  // [sample * ln_stride + column]
     const float* ln_scale = nullptr;

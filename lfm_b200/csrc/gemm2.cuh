@@ -240,14 +240,14 @@ LFM_DEVICE void stage_row_bf16_half(uint8_t* stg, int lane, const float* f, int 
 }
 
 // LayerNorm + adaLN modulate of `nrows` rows of the fp32 residual stream (just completed by the reduce-adds of this
-// launch, so read through L2: ld.global.cg), executed by the 4 finisher warps of one CTA: 2 rows per warp in flight.
+// launch, so read through L2: ld.global.cg), executed by ONE finisher warp per 4-row unit: 2 rows in flight.
 // Same arithmetic as ln_modulate_kernel (two-pass statistics in registers, eps 1e-6).
-LFM_DEVICE void ln_finish_rows(const GemmEpi& ep, int row0, int nrows, int M, int D, int wf, int lane) {
+LFM_DEVICE void ln_finish_rows(const GemmEpi& ep, int row0, int nrows, int M, int D, int lane) {
     constexpr int MAXV = 9;  // D <= 1152
     const int nv = D / 128;
     const float* x = static_cast<const float*>(ep.out);
     const float inv_d = 1.0f / static_cast<float>(D);
-    for (int r = row0 + 2 * wf; r < row0 + nrows; r += 8) {
+    for (int r = row0; r < row0 + nrows; r += 2) {
         float4 v[2][MAXV];
         bool ok[2];
 #pragma unroll
@@ -329,14 +329,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
     uint64_t* tmem_empty = bars + 2 * kG2Stages + 2;  // [2] leader only: 16 epilogue warps (8 per CTA) arrive
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kG2Stages + 4);
     uint8_t* smem_stage = smem + kG2Stages * kG2StageBytes + 1024;  // 8 x 4 KB epilogue staging tiles (1024-aligned)
-    // LayerNorm finisher hand-off (FIN): completed row blocks queued by this CTA's epilogue warps for its finisher warps
-    __shared__ int fin_queue[16];  // -1 = empty
-    __shared__ int fin_pushed, fin_exit;
-    if (FIN && threadIdx.x < 16) fin_queue[threadIdx.x] = -1;
-    if (FIN && threadIdx.x == 0) {
-        fin_pushed = 0;
-        fin_exit = 0;
-    }
+    constexpr int kFinUnits = 64;  // LayerNorm finisher: work units (of 4 rows) per 256-row block
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -403,6 +396,11 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();     // everything above overlapped the tail of the previous kernel; its outputs are complete from here on
     pdl_trigger();
+    if (FIN && ep.fin_ctl != nullptr && blockIdx.x == 0 && warp == 3) {
+        // prepare the control block of the NEXT finisher launch (the previous user of that block has completed)
+        int* other = ep.fin_ctl + (ep.fin_set ^ 1) * ep.fin_stride;
+        for (int i = lane; i < ep.fin_stride; i += 32) other[i] = i < 4 ? 0 : -1;
+    }
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -616,7 +614,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 acc = 0;
                 acc_phase ^= 1;
             }
-            if (FIN && EPI == EPI_GATE_RESID_F32 && lane == 0) {
+            if (FIN && EPI == EPI_GATE_RESID_F32 && ep.ln_out != nullptr && lane == 0) {
                 // this warp's share of the tile is in the residual stream once its reduce-adds have been performed
                 tma_store_wait<0>();
                 fence_proxy_async();
@@ -626,37 +624,33 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
                 if (old + units == 32 * n_blocks) {                          // 16 warps x 2 units x column tiles: block complete
                     atomicExch(ep.rb_count + m_blk, 0);                      // ready for the next launch
                     __threadfence();                                         // acquire
-                    const int slot = atomicAdd(&fin_pushed, 1);              // reserve a queue slot, then publish the block index
-                    atomicExch(&fin_queue[slot & 15], m_blk);
+                    int* ctl = ep.fin_ctl + ep.fin_set * ep.fin_stride;
+                    const int slot = atomicAdd(ctl + 1, 1);                  // reserve a queue slot, then publish the block index
+                    atomicExch(ctl + 4 + slot, m_blk);
                 }
             }
         }
         if (lane == 0) tma_store_wait<0>();  // all global writes of this warp are complete before the CTA exits
-        if (FIN && lane == 0) {
-            __threadfence_block();
-            atomicAdd(&fin_exit, 1);
-        }
     } else if (FIN && warp >= 12) {
-        // ===================== LayerNorm finisher: 4 warps, woken by this CTA's epilogue warps =====================
-        const int wf = warp - 12;
-        volatile int* vp = &fin_pushed;
-        volatile int* ve = &fin_exit;
-        volatile int* vq = fin_queue;
-        int done = 0;
-        for (;;) {
-            if (*vp <= done) {
-                if (*ve == 8 && *vp <= done) break;  // all epilogue warps of this CTA have left their loops: no more pushes
-                __nanosleep(256);
-                continue;
+        // ===================== LayerNorm finisher: 4 warps per CTA pulling 4-row units from the global queue =====================
+        if (ep.ln_out != nullptr) {
+            int* ctl = ep.fin_ctl + ep.fin_set * ep.fin_stride;
+            const int total_units = m_blocks * kFinUnits;
+            for (;;) {
+                int u = 0;
+                if (lane == 0) u = atomicAdd(ctl, 1);
+                u = __shfl_sync(0xffffffffu, u, 0);
+                if (u >= total_units) break;
+                const int q = u / kFinUnits, part = u % kFinUnits;
+                int mb = 0;
+                if (lane == 0) {
+                    volatile int* vq = ctl + 4 + q;
+                    while ((mb = *vq) < 0) __nanosleep(128);   // the q-th completed block has not been published yet
+                }
+                mb = __shfl_sync(0xffffffffu, mb, 0);
+                __threadfence();                               // acquire: the rows of block mb are complete and visible
+                ln_finish_rows(ep, mb * 256 + part * (256 / kFinUnits), 256 / kFinUnits, M, N, lane);
             }
-            int mb;
-            while ((mb = vq[done & 15]) < 0) __nanosleep(32);  // the slot is reserved; its value arrives a moment later
-            __syncwarp();
-            asm volatile("bar.sync 2, 128;" ::: "memory");     // all 4 finisher warps have read the slot
-            if (warp == 12 && lane == 0) vq[done & 15] = -1;
-            ++done;
-            __threadfence();                                    // acquire: the rows of block mb are complete and visible
-            ln_finish_rows(ep, mb * 256, 256, M, N, wf, lane);
         }
     }
 

@@ -297,7 +297,7 @@ static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUte
         const ConvGeom cg{0, 0, 0, 0, 1};
         if (epi == EPI_BIAS_BF16) return launch_gemm2_inst<EPI_BIAS_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
         if (epi == EPI_BIAS_GELU_BF16) return launch_gemm2_inst<EPI_BIAS_GELU_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
-        if (epi == EPI_GATE_RESID_F32 && ep.ln_out != nullptr) return launch_gemm2_fin(s, ta, tb, *tout, M, N, K, ep, tbh);
+        if (epi == EPI_GATE_RESID_F32 && ep.fin_ctl != nullptr) return launch_gemm2_fin(s, ta, tb, *tout, M, N, K, ep, tbh);
         if (epi == EPI_GATE_RESID_F32) return launch_gemm2_inst<EPI_GATE_RESID_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
         if (epi == EPI_BIAS_F32) return launch_gemm2_inst<EPI_BIAS_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
         return cudaErrorInvalidValue;
@@ -407,6 +407,8 @@ struct lfm_ctx {
     int l2_hint = 0;       // LFM_L2_HINT: evict_last L2 policy on the residual stream's TMA traffic (measured: no gain)
     int ln_fuse = 1;       // LFM_LN_FUSE: LayerNorm + modulate of the next layer produced by the residual GEMM's finisher warps
     int* rb_count = nullptr;  // per 256-row block arrival counters of the finisher (GemmEpi::rb_count)
+    int* fin_ctl = nullptr;   // two control blocks {ticket, tail, -, -, queue[m_blocks]} of the finisher (GemmEpi::fin_ctl)
+    int fin_stride = 0;
     int bn_qkv = 256, bn_proj = 256, bn_fc1 = 256, bn_fc2 = 256, bn_mod = 256;
 
     std::unordered_map<std::string, ParamSlot> params;
@@ -702,6 +704,14 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
     if (dev_alloc(ctx, &ctx->h1, (size_t)R * D)) return 1;
     if (dev_alloc(ctx, &ctx->v_net, (size_t)R * ctx->chw)) return 1;
     if (dev_alloc(ctx, &ctx->rb_count, (M + 255) / 256 + 1)) return 1;
+    {
+        ctx->fin_stride = 4 + (int)((M + 255) / 256) + 4;
+        if (dev_alloc(ctx, &ctx->fin_ctl, (size_t)2 * ctx->fin_stride)) return 1;
+        std::vector<int> init((size_t)2 * ctx->fin_stride, -1);
+        for (int sset = 0; sset < 2; ++sset)
+            for (int i = 0; i < 4; ++i) init[(size_t)sset * ctx->fin_stride + i] = 0;
+        CUDA_OK(cudaMemcpy(ctx->fin_ctl, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     if (alloc_solver_state(ctx, R)) return 1;
 
     // default: the CTA-pair kernel for every token-level GEMM (LFM_BN_* = 128 / 256 selects the 1-CTA kernel)
@@ -799,6 +809,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
     // LayerNorm fusion: the proj / fc2 GEMMs (pair kernel, full rows: N == D) also emit the LayerNorm-modulated operand of
     // the layer that follows them; only the very first LayerNorm of the network is a stand-alone pass.
     const bool fuse = ctx->ln_fuse && ctx->bn_proj == kGemmPair && ctx->bn_fc2 == kGemmPair;  // (the finisher lives in gemm2 only)
+    int fin_set = 0;  // the 2 L finisher launches of one evaluation alternate between the two control blocks, starting at 0
     static const int g2_flags = env_int("LFM_G2_FLAGS", 0) & 8;  // 8: bf16 epilogues store straight from registers (A/B switch)
     for (int l = 0; l < L; ++l) {
         BlockW& b = ctx->blk[l];
@@ -831,6 +842,10 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
             ep.l2_keep = ctx->l2_hint;
             if (fuse) {  // x += gate_msa * proj(...), then xn = LN(x) * (1 + scale_mlp) + shift_mlp   (models/DiT.py:129-130)
                 ep.rb_count = ctx->rb_count;
+                ep.fin_ctl = ctx->fin_ctl;
+                ep.fin_stride = ctx->fin_stride;
+                ep.fin_set = fin_set;
+                fin_set ^= 1;
                 ep.ln_out = ctx->xn;
                 ep.ln_shift = mb + 3 * D;
                 ep.ln_scale = mb + 4 * D;
@@ -855,13 +870,19 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
             GemmEpi ep{b.b_fc2, ctx->x_tok, D, mb + 5 * D, Nmod, T};
             ep.reverse_m = next_dir();
             ep.l2_keep = ctx->l2_hint;
-            if (fuse && l + 1 < L) {  // x += gate_mlp * fc2(...), then the NEXT block's xn = LN(x) * (1 + scale_msa) + shift_msa
-                const float* mn = ctx->mod + (size_t)(l + 1) * 6 * D;
+            if (fuse) {  // x += gate_mlp * fc2(...), then the NEXT block's xn = LN(x) * (1 + scale_msa) + shift_msa
                 ep.rb_count = ctx->rb_count;
-                ep.ln_out = ctx->xn;
-                ep.ln_shift = mn;
-                ep.ln_scale = mn + D;
-                ep.ln_stride = Nmod;
+                ep.fin_ctl = ctx->fin_ctl;
+                ep.fin_stride = ctx->fin_stride;
+                ep.fin_set = fin_set;
+                fin_set ^= 1;
+                if (l + 1 < L) {  // (the last block's launch only keeps the control blocks alternating: FinalLayer has its own LayerNorm)
+                    const float* mn = ctx->mod + (size_t)(l + 1) * 6 * D;
+                    ep.ln_out = ctx->xn;
+                    ep.ln_shift = mn;
+                    ep.ln_scale = mn + D;
+                    ep.ln_stride = Nmod;
+                }
             }
             CUDA_OK(launch_gemm(s, ctx->tm_hmid, b.tm_fc2, M, D, Hd, EPI_GATE_RESID_F32, ctx->bn_fc2, ep, &ctx->tmo_xtok, &b.tmh_fc2, &ctx->tm64_hmid));
             ctx->launches++;
