@@ -6,7 +6,8 @@
 
 Same flags, defaults and modes as the reference (test_flow_latent.py:302-408): default "inference" (one batch ->
 image grid), ``--compute_nfe``, ``--measure_time``, ``--compute_fid`` (generation loop with the reference's file
-indexing; the FID statistic itself is the reference's pytorch_fid and is out of this build's scope).  Under
+indexing; with ``--inception_weights FILE`` the FID itself is computed on the device from the decoded uint8 batches,
+lfm_b200/fid.py, and printed / logged as the reference does, test_flow_latent.py:274-282).  Under
 ``torchrun`` (RANK/WORLD_SIZE set) it behaves like test_flow_latent_ddp.py: one process per GPU, per-rank batches,
 seed = seed + rank, file index j * world + rank + total.
 
@@ -95,6 +96,11 @@ def build_parser():
                    help="native: lfm_b200.AutoencoderKL (sm_100a kernels); diffusers: the reference's torch module")
     p.add_argument("--synthetic_vae", type=int, default=None, metavar="SEED", help="seeded decoder weights instead of a checkpoint")
     p.add_argument("--writer_threads", type=int, default=8, help="JPEG encoder threads of the --compute_fid loop")
+    p.add_argument("--inception_weights", type=str, default=None, metavar="FILE",
+                   help="local pt_inception-2015-12-05-6726825d.pth: compute the FID on the device in the --compute_fid loop")
+    p.add_argument("--synthetic_inception", type=int, default=None, metavar="SEED",
+                   help="seeded Inception weights (plumbing check only; the number is meaningless)")
+    p.add_argument("--no_save", action="store_true", help="--compute_fid: do not write the JPEG files")
     p.add_argument("--out_dir", type=str, default=".")
     p.add_argument("--measure_reps", type=int, default=300)
     return p
@@ -118,6 +124,23 @@ def load_model(args, device):
     model = model.to_empty(device="cpu")
     model.load_state_dict(sd, strict=True)
     return model.to(device).eval()
+
+
+_STAT_BY_DATASET = {      # test_flow_latent.py:113-126
+    "cifar10": "cifar10_train_stat.npy", "celeba_256": "celebahq_stat.npy", "lsun_church": "lsun_church_stat.npy",
+    "ffhq_256": "ffhq_stat.npy", "lsun_bedroom": "lsun_bedroom_stat.npy", "latent_imagenet_256": "imagenet_stat.npy",
+    "imagenet_256": "imagenet_stat.npy",
+}
+
+
+def real_stats_path(args):
+    """The dataset statistics file, chosen as the reference does (by --dataset, else --real_img_dir); when
+    --real_img_dir names an existing file it wins, so the statistics need not live under ./pytorch_fid."""
+    if os.path.isfile(args.real_img_dir):
+        return args.real_img_dir
+    if args.dataset in _STAT_BY_DATASET:
+        return os.path.join("pytorch_fid", _STAT_BY_DATASET[args.dataset])
+    return args.real_img_dir
 
 
 def load_vae(args, device):
@@ -296,7 +319,15 @@ def main(argv=None):
         if world > 1:
             torch.distributed.barrier()
         total = 0
-        sink = ImageSink(device, args.writer_threads) if vae is not None else None
+        sink = ImageSink(device, args.writer_threads) if vae is not None and not args.no_save else None
+        fid_acc = None
+        if args.inception_weights is not None or args.synthetic_inception is not None:
+            if vae is None:
+                raise ValueError("the FID needs decoded images: drop --no_decode")
+            from . import fid as lfid
+            net = (lfid.FIDInception.from_file(args.inception_weights) if args.inception_weights is not None
+                   else lfid.FIDInception(lfid.synthetic_inception_state_dict(args.synthetic_inception)))
+            fid_acc = lfid.FIDAccumulator(net, device)
         for i in range(iters):
             out = run_sampling(n, generator, as_uint8=True)
             if vae is None:
@@ -305,7 +336,11 @@ def main(argv=None):
             else:
                 if out.dtype != torch.uint8:      # the torch VAE: the reference's expression (test_flow_latent_ddp.py:131-135)
                     out = (torch.clamp((out + 1.0) / 2.0, 0, 1) * 255.0).permute(0, 2, 3, 1).to(torch.uint8)
-                sink.put(out, ["{}/{}.jpg".format(save_dir, ldist.file_index(j, world, rank, total)) for j in range(out.shape[0])])
+                if fid_acc is not None:
+                    fid_acc.update(out)           # features + running statistics on the device; no file round trip
+                if sink is not None:
+                    sink.put(out, ["{}/{}.jpg".format(save_dir, ldist.file_index(j, world, rank, total))
+                                   for j in range(out.shape[0])])
             total += n * world
             if rank == 0:
                 print("generating batch ", i)
@@ -313,8 +348,15 @@ def main(argv=None):
             sink.close()
         if world > 1:
             torch.distributed.barrier()
-        if rank == 0:
-            print("samples written to", save_dir, "- run the reference's pytorch_fid on them for the FID statistic")
+        if fid_acc is not None:
+            value = fid_acc.compute(real_stats_path(args))       # one all-reduce of the statistics across the ranks
+            if rank == 0:
+                print("FID = {}".format(value))                   # test_flow_latent.py:280-282
+                if args.output_log:
+                    with open(args.output_log, "a") as f:
+                        f.write("Epoch = {}, FID = {}\n".format(args.epoch_id, value))
+        elif rank == 0:
+            print("samples written to", save_dir, "- pass --inception_weights FILE for the FID, or run pytorch_fid on them")
         return 0
 
     # default: one batch; every rank samples (and decodes) its shard and ONE all-gather assembles the result on all

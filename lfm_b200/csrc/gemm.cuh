@@ -40,25 +40,25 @@ struct GemmEpi {
     int reverse_m = 0;
     // Pair kernel, EPI_GATE_RESID_F32: the TMA reduce-add into the residual stream carries the evict_last L2 policy.
     int l2_keep = 0;
-    // Pair kernel with the LayerNorm finisher (gemm2_bf16_tcgen05<EPI_GATE_RESID_F32, true>; N == ldo == D): once every
-    // column tile of a 256-row block of the residual stream has been added, the CTA that added the last one also
-    // produces the NEXT layer's operand  ln_out = LayerNorm(x) * (1 + ln_scale) + ln_shift  (bf16; models/DiT.py:20-21,
-    // 129-130) for those rows while they are still in L2 - the stand-alone LayerNorm pass over x disappears.
-    // rb_count[m_blk] counts arrivals (zero on entry; reset by the finisher).
     // Pair kernel, EPI_BIAS_F32: out = addend + acc + bias, the residual connection of a convolutional block added by
     // the SM (fp32 [M, ldo]; may alias out) - so that the block's OUTPUT statistics (gn_bins) can be taken in the same
     // epilogue, which a reduce-add performed at L2 never sees.
     const float* addend = nullptr;
-    int dbg_flags = 0;  // measurement aids (LFM_G2_DBG): 1 = the epilogue releases the accumulator without draining it
-    // Completed blocks are published in a GLOBAL queue and every CTA's finisher warps pull 4-row units from it (ticket
-    // counter): the LayerNorm work is spread over the whole chip instead of landing on whichever CTA arrived last (round 2's
-    // first version: 2.6x slower end to end).  fin_ctl: two control blocks of fin_stride ints {ticket, tail, -, -,
-    // queue[m_blocks]}; a launch uses block fin_set and re-initialises the OTHER one for the finisher launch after it.
+    int dbg_flags = 0;  // measurement aids (LFM_G2_DBG, profiles/r2g_gemm2_epilogue_cost.md): 1 accumulators released undrained,
+                        // 2 TMEM reads only, 4 no global stores, 8 bf16 rows stored straight from registers
+    // Pair kernel with the LayerNorm finisher (gemm2_bf16_tcgen05<EPI_GATE_RESID_F32, true>; N == ldo == D): once every
+    // column tile of a 256-row block of the residual stream has been added, the block is published in a GLOBAL queue and
+    // the finisher warps of ALL CTAs pull 4-row units from it (ticket counter) and produce the NEXT layer's operand
+    // ln_out = LayerNorm(x) * (1 + ln_scale) + ln_shift (bf16; models/DiT.py:20-21, 129-130) while the rows are still in
+    // L2 - the stand-alone LayerNorm pass over x disappears.  (Round 2's first version let the CTA that arrived last do the
+    // whole block: 2.6x slower end to end.)  rb_count[m_blk] counts arrivals (zero on entry; reset by the last arriver).
+    // fin_ctl: two control blocks of fin_stride ints {ticket, tail, -, -, queue[m_blocks]}; a launch uses block fin_set and
+    // re-initialises the OTHER one for the finisher launch after it (they alternate 0 / 1 within a network evaluation).
     int* rb_count = nullptr;
     int* fin_ctl = nullptr;
     int fin_stride = 0;
     int fin_set = 0;
-    __nv_bfloat16* ln_out = nullptr;
+    __nv_bfloat16* ln_out = nullptr;  // nullptr: this launch only keeps the control blocks alternating
     const float* ln_shift = nullptr;  // [sample * ln_stride + column]
     const float* ln_scale = nullptr;
     int ln_stride = 0;

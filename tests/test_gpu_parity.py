@@ -733,4 +733,15 @@ def test_cli_decode_and_generation_loop(dev, tmp_path):
     assert files == [f"{i}.jpg" for i in range(6)]
     assert all(Image.open(os.path.join(d, f)).size == (256, 256) for f in files)
     assert cli.main(common + ["--measure_time", "--measure_reps", "3"]) == 0
+    # FID on the device inside the same loop (seeded Inception weights: plumbing, not a meaningful number): statistics
+    # file in the reference's pickled-dict layout, the value printed and appended to --output_log (test_flow_latent.py:280-282)
+    import numpy as np
+    stat, log = os.path.join(out, "stat.npy"), os.path.join(out, "fid.log")
+    rng = np.random.RandomState(0)
+    feats = rng.rand(64, 2048)
+    np.save(stat, {"mu": feats.mean(0), "sigma": np.cov(feats, rowvar=False)}, allow_pickle=True)
+    assert cli.main(common + ["--batch_size", "3", "--n_sample", "6", "--compute_fid", "--synthetic_inception", "1", "--no_save",
+                              "--real_img_dir", stat, "--output_log", log, "--dataset", "custom"]) == 0
+    line = open(log).read().strip()
+    assert line.startswith("Epoch = 1000, FID = ") and np.isfinite(float(line.split("FID = ")[1])) and float(line.split("FID = ")[1]) > 0
 
