@@ -30,8 +30,11 @@ struct GemmEpi {
     int gate_stride;      // elements between samples in the modulation table
     int rows_per_sample;  // tokens per sample (b = row / rows_per_sample)
     // Optional (pair kernel, EPI_BIAS_F32): GroupNorm statistics of the OUTPUT accumulated in the epilogue -
-    // bins[(row / gn_hw) * 64 + 2 g + {0,1}] += {sum, sum of squares} of group g = column / gn_cpg, as 2^28 fixed point
-    // (integer atomics => the result does not depend on the order of arrival: deterministic).
+    // bins[((row / gn_hw) * kGnBinReplicas + r) * 64 + 2 g + {0,1}] += {sum, sum of squares} of group g = column / gn_cpg, as
+    // 2^28 fixed point (integer atomics => the result does not depend on the order of arrival: deterministic).  r is any of
+    // kGnBinReplicas copies (chosen per warp; the consumer adds them up - integers, so still exact): persistent CTAs walk the
+    // tiles of ONE image together, and with a single copy every atomic of the chip queued on the same four 128-byte lines
+    // (a 128-channel 256 x 256 VAE layer: 2.1 M atomics, +525 us on a 410 us convolution; profiles/r2l_vae_launches.md).
     unsigned long long* gn_bins = nullptr;
     int gn_cpg = 0;
     int gn_hw = 1;
@@ -63,6 +66,7 @@ struct GemmEpi {
     const float* ln_scale = nullptr;
     int ln_stride = 0;
 };
+constexpr int kGnBinReplicas = 16;
 constexpr double kGnFixScale = 268435456.0;  // 2^28
 
 constexpr int kGemmBlockM = 128;

@@ -205,7 +205,8 @@ LFM_DEVICE void gn_accumulate_chunk(const float* f, bool row_ok, int n0, unsigne
 }
 LFM_DEVICE void gn_accumulate(const float* f, const GemmEpi& ep, int row, int M, int n0, int N, int lane) {
     if (n0 >= N) return;
-    unsigned long long* bins_b = ep.gn_bins + static_cast<size_t>((row < M ? row : M - 1) / ep.gn_hw) * 64;
+    const int rep = static_cast<int>((blockIdx.x * 5u + (threadIdx.x >> 5)) % kGnBinReplicas);
+    unsigned long long* bins_b = ep.gn_bins + (static_cast<size_t>((row < M ? row : M - 1) / ep.gn_hw) * kGnBinReplicas + rep) * 64;
     bins_b = reinterpret_cast<unsigned long long*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(bins_b), 0));
     const bool ok = row < M;
     switch (ep.gn_cpg) {

@@ -108,14 +108,25 @@ gn_apply_kernel(GnApplyArgs a) {
     extern __shared__ float s_coef[];  // [2][C]: y = x * A[c] + Bc[c]   (GroupNorm affine and FiLM folded per channel)
     __shared__ float s_mean[32], s_rstd[32];
     constexpr int C = J * 128, cpg = C / 32;
-    constexpr int JB = J >= 4 ? 4 : J;  // float4 loads issued before the first store
+    // Eight 16-byte loads per lane are issued before the first store (one pixel of C <= 256 channels is only 1-2 loads per lane:
+    // a warp with a single 512-byte request in flight leaves the kernel latency-bound at ~40 % of the HBM rate), so a warp
+    // takes PIXB consecutive pixels per iteration.
+    constexpr int NL = 8;
+    constexpr int JB = J >= NL ? NL : J;
+    constexpr int PIXB = J >= NL ? 1 : NL / J;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     if (threadIdx.x < 32) {
         double S = 0.0, Q = 0.0;
         if (a.bins != nullptr) {  // statistics accumulated by the producing convolution's epilogue (integer, order-free)
-            S = static_cast<double>(static_cast<long long>(a.bins[static_cast<size_t>(b) * 64 + 2 * threadIdx.x])) / 268435456.0;
-            Q = static_cast<double>(static_cast<long long>(a.bins[static_cast<size_t>(b) * 64 + 2 * threadIdx.x + 1])) / 268435456.0;
+            long long si = 0, qi = 0;  // the replicas are integers: their sum is exact whatever the arrival order was
+            for (int r = 0; r < kGnBinReplicas; ++r) {
+                const unsigned long long* bp = a.bins + (static_cast<size_t>(b) * kGnBinReplicas + r) * 64 + 2 * threadIdx.x;
+                si += static_cast<long long>(bp[0]);
+                qi += static_cast<long long>(bp[1]);
+            }
+            S = static_cast<double>(si) / 268435456.0;
+            Q = static_cast<double>(qi) / 268435456.0;
         } else {
             for (int c = 0; c < a.nchunk; ++c) {  // fixed order => deterministic
                 S += a.partial[(static_cast<size_t>(b) * a.nchunk + c) * 64 + 2 * threadIdx.x];
@@ -145,39 +156,47 @@ gn_apply_kernel(GnApplyArgs a) {
     }
     __syncthreads();
     const bool act = a.act != 0;
-    for (int p = blockIdx.x * 8 + warp; p < a.HW; p += gridDim.x * 8) {
-        const size_t pix = static_cast<size_t>(b) * a.HW + p;
+    for (int p0 = (blockIdx.x * 8 + warp) * PIXB; p0 < a.HW; p0 += gridDim.x * 8 * PIXB) {
+        const size_t pix0 = static_cast<size_t>(b) * a.HW + p0;
 #pragma unroll
         for (int j0 = 0; j0 < J; j0 += JB) {
-            float4 vv[JB];
+            float4 vv[PIXB][JB];
 #pragma unroll
-            for (int u = 0; u < JB; ++u)
-                if (j0 + u < J) {
-                    if (a.src_bf16 != nullptr) {
-                        const uint2 r = *reinterpret_cast<const uint2*>(a.src_bf16 + pix * C + 128 * (j0 + u) + 4 * lane);
-                        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
-                        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
-                        vv[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                    } else {
-                        vv[u] = src2_load(a.src, pix, 128 * (j0 + u) + 4 * lane);
+            for (int q = 0; q < PIXB; ++q)
+#pragma unroll
+                for (int u = 0; u < JB; ++u)
+                    if (j0 + u < J && p0 + q < a.HW) {
+                        const size_t off = (pix0 + q) * C + 128 * (j0 + u) + 4 * lane;
+                        if (a.src_bf16 != nullptr) {
+                            const uint2 r = *reinterpret_cast<const uint2*>(a.src_bf16 + off);
+                            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+                            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+                            vv[q][u] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                        } else {
+                            vv[q][u] = src2_load(a.src, pix0 + q, 128 * (j0 + u) + 4 * lane);
+                        }
                     }
-                }
 #pragma unroll
             for (int u = 0; u < JB; ++u) {
                 if (j0 + u < J) {
                     const int ch = 128 * (j0 + u) + 4 * lane;
-                    const float4 v = vv[u];
                     const float4 A = *reinterpret_cast<const float4*>(s_coef + ch);
                     const float4 Bc = *reinterpret_cast<const float4*>(s_coef + C + ch);
-                    float y0 = fmaf(v.x, A.x, Bc.x), y1 = fmaf(v.y, A.y, Bc.y), y2 = fmaf(v.z, A.z, Bc.z), y3 = fmaf(v.w, A.w, Bc.w);
-                    if (act) {
-                        y0 = silu(y0), y1 = silu(y1), y2 = silu(y2), y3 = silu(y3);
+#pragma unroll
+                    for (int q = 0; q < PIXB; ++q) {
+                        if (p0 + q < a.HW) {
+                            const float4 v = vv[q][u];
+                            const size_t off = (pix0 + q) * C + ch;
+                            float y0 = fmaf(v.x, A.x, Bc.x), y1 = fmaf(v.y, A.y, Bc.y), y2 = fmaf(v.z, A.z, Bc.z), y3 = fmaf(v.w, A.w, Bc.w);
+                            if (act) {
+                                y0 = silu_fast(y0), y1 = silu_fast(y1), y2 = silu_fast(y2), y3 = silu_fast(y3);
+                            }
+                            *reinterpret_cast<uint2*>(a.out + off) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                            if (a.copy_out != nullptr) *reinterpret_cast<float4*>(a.copy_out + off) = v;
+                            if (a.raw_out != nullptr)
+                                *reinterpret_cast<uint2*>(a.raw_out + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                        }
                     }
-                    *reinterpret_cast<uint2*>(a.out + pix * C + ch) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-                    if (a.copy_out != nullptr) *reinterpret_cast<float4*>(a.copy_out + pix * C + ch) = v;
-                    if (a.raw_out != nullptr)
-                        *reinterpret_cast<uint2*>(a.raw_out + pix * C + ch) =
-                            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
                 }
             }
         }
@@ -329,20 +348,27 @@ __global__ void nhwc4_to_nchw_kernel(const float* __restrict__ in, float* __rest
 }
 
 // Upsample: nearest x2 of the fp32 stream -> bf16 operand of the following conv3x3 (unet.py:92-99).
-__global__ void upsample2x_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C) {
+// One thread per INPUT float4: one 16-byte load, four 8-byte stores (the 2 x 2 output pixels); grid (ceil(W * C/4 / 256), B * H),
+// so the only index arithmetic is one 32-bit division (the first version decoded a flat 64-bit output index per thread: three
+// 64-bit divisions per 8 bytes stored, 2.3 TB/s).
+__global__ void __launch_bounds__(256)
+upsample2x_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C) {
     pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
     pdl_trigger();
-    const size_t n4 = static_cast<size_t>(B) * 2 * H * 2 * W * (C / 4);
-    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const int c4 = static_cast<int>(i % (C / 4));
-    size_t r = i / (C / 4);
-    const int w2 = static_cast<int>(r % (2 * W));
-    r /= (2 * W);
-    const int h2 = static_cast<int>(r % (2 * H));
-    const int b = static_cast<int>(r / (2 * H));
-    const float4 v = *reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * H + h2 / 2) * W + w2 / 2) * C + c4 * 4);
-    *reinterpret_cast<uint2*>(y + i * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const unsigned c4n = static_cast<unsigned>(C) >> 2;
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= static_cast<unsigned>(W) * c4n) return;
+    const unsigned w = i / c4n, c4 = i - w * c4n;
+    const unsigned bh = blockIdx.y;  // b * H + h
+    const unsigned b = bh / static_cast<unsigned>(H), h = bh - b * static_cast<unsigned>(H);
+    const float4 v = *reinterpret_cast<const float4*>(x + (static_cast<size_t>(bh) * W + w) * C + c4 * 4);
+    const uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    __nv_bfloat16* row0 = y + ((static_cast<size_t>(b) * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c4 * 4;
+    __nv_bfloat16* row1 = row0 + static_cast<size_t>(2) * W * C;
+    *reinterpret_cast<uint2*>(row0) = o;
+    *reinterpret_cast<uint2*>(row0 + C) = o;
+    *reinterpret_cast<uint2*>(row1) = o;
+    *reinterpret_cast<uint2*>(row1 + C) = o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -655,15 +681,16 @@ __global__ void resample2x_kernel(const __nv_bfloat16* __restrict__ a_in, __nv_b
     pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
     pdl_trigger();
     const int Ho = UP ? 2 * H : H / 2, Wo = UP ? 2 * W : W / 2;
-    const size_t n4 = static_cast<size_t>(B) * Ho * Wo * (C / 4);
+    const size_t n4 = static_cast<size_t>(B) * Ho * Wo * (C / 4);  // < 2^32 (checked by the host): 32-bit index arithmetic
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    const int c = static_cast<int>(i % (C / 4)) * 4;
-    size_t r = i / (C / 4);
-    const int wo = static_cast<int>(r % Wo);
-    r /= Wo;
-    const int ho = static_cast<int>(r % Ho);
-    const int b = static_cast<int>(r / Ho);
+    const unsigned c4n = static_cast<unsigned>(C) >> 2, i32 = static_cast<unsigned>(i);
+    unsigned r = i32 / c4n;
+    const int c = static_cast<int>(i32 - r * c4n) * 4;
+    const unsigned r2 = r / static_cast<unsigned>(Wo);
+    const int wo = static_cast<int>(r - r2 * Wo);
+    const int b = static_cast<int>(r2 / static_cast<unsigned>(Ho));
+    const int ho = static_cast<int>(r2 - static_cast<unsigned>(b) * Ho);
     if (UP) {
         const size_t src = ((static_cast<size_t>(b) * H + ho / 2) * W + wo / 2) * C + c;
         *reinterpret_cast<uint2*>(a_out + i * 4) = *reinterpret_cast<const uint2*>(a_in + src);

