@@ -179,28 +179,56 @@ LFM_DEVICE void epilogue_math(const uint32_t* v, float* f, const GemmEpi& ep, in
     }
 }
 
-// GroupNorm statistics of one 32-column chunk (see GemmEpi::gn_bins): per-thread sums over each group's columns,
-// warp reduction over the 32 rows, one 64-bit integer atomic per (group, moment).
+// GroupNorm statistics of one 32-column chunk (see GemmEpi::gn_bins): per-thread sums over each group's columns, then ONE
+// halving butterfly over the 32 rows for all V = 2 * groups values at once - at every step a lane keeps half of its values and
+// hands the other half to its partner, so 16 values cost 8 + 4 + 2 + 1 + 1 = 16 shuffles (one warp_sum per value: 80) and end up
+// on 16 different lanes, which issue their 64-bit integer atomics in ONE instruction.  (The first version - a warp_sum and a
+// lane-0 atomic per value - made a 128-channel convolution's epilogue cost more than its mainloop: 866 us vs 406 us.)
+template <int V>
+LFM_DEVICE float halving_reduce(float (&v)[V], int lane) {
+    int width = V;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (width > 1) {
+            width >>= 1;
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < V / 2; ++i)
+                if (i < width) {
+                    const float send = hi ? v[i] : v[i + width];
+                    const float keep = hi ? v[i + width] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
+    }
+    return v[0];  // the total of value (lane >> (5 - log2 V)); every lane of that group of lanes holds it
+}
 template <int CPG>
 LFM_DEVICE void gn_accumulate_chunk(const float* f, bool row_ok, int n0, unsigned long long* bins_b, int lane) {
     constexpr int NG = CPG >= 32 ? 1 : 32 / CPG;   // groups inside this chunk
     constexpr int W = CPG >= 32 ? 32 : CPG;        // columns per group inside this chunk
+    constexpr int V = 2 * NG;                      // {sum, sum of squares} per group
+    constexpr int SH = V == 16 ? 1 : V == 8 ? 2 : V == 4 ? 3 : 4;   // 5 - log2(V)
+    float v[V];
 #pragma unroll
     for (int gi = 0; gi < NG; ++gi) {
         float s = 0.f, q = 0.f;
 #pragma unroll
         for (int k = 0; k < W; ++k) {
-            const float v = row_ok ? f[gi * W + k] : 0.f;
-            s += v;
-            q = fmaf(v, v, q);
+            const float x = row_ok ? f[gi * W + k] : 0.f;
+            s += x;
+            q = fmaf(x, x, q);
         }
-        s = warp_sum(s);
-        q = warp_sum(q);
-        if (lane == 0) {
-            const int g = (n0 + gi * W) / CPG;
-            atomicAdd(bins_b + 2 * g, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(s) * kGnFixScale)));
-            atomicAdd(bins_b + 2 * g + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(q) * kGnFixScale)));
-        }
+        v[2 * gi] = s;
+        v[2 * gi + 1] = q;
+    }
+    const float total = halving_reduce<V>(v, lane);
+    if ((lane & ((1 << SH) - 1)) == 0) {
+        const int idx = lane >> SH;
+        const int g = (n0 + (idx >> 1) * W) / CPG;
+        atomicAdd(bins_b + 2 * g + (idx & 1), static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(total) * kGnFixScale)));
     }
 }
 LFM_DEVICE void gn_accumulate(const float* f, const GemmEpi& ep, int row, int M, int n0, int N, int lane) {

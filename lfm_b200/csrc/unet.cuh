@@ -101,7 +101,7 @@ struct GnApplyArgs {
     __nv_bfloat16* raw_out;     // nullptr or bf16 [B, HW, C]
 };
 template <int J>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)  // 4 blocks per SM resident: the host sizes the grid to ONE wave of 4 x SMs blocks
 gn_apply_kernel(GnApplyArgs a) {
     pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
     pdl_trigger();
@@ -111,7 +111,7 @@ gn_apply_kernel(GnApplyArgs a) {
     // Eight 16-byte loads per lane are issued before the first store (one pixel of C <= 256 channels is only 1-2 loads per lane:
     // a warp with a single 512-byte request in flight leaves the kernel latency-bound at ~40 % of the HBM rate), so a warp
     // takes PIXB consecutive pixels per iteration.
-    constexpr int NL = 8;
+    constexpr int NL = J <= 4 ? 8 : 4;  // wide channel counts only occur on the small grids; 4 keeps them inside 64 registers
     constexpr int JB = J >= NL ? NL : J;
     constexpr int PIXB = J >= NL ? 1 : NL / J;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
