@@ -2,6 +2,7 @@
 // Activations are NHWC: an fp32 "stream" tensor per block output (skip connections, residual adds) and bf16 operand
 // tensors feeding the tcgen05 implicit-GEMM convolutions (gemm2.cuh with a 4-D TMA im2col producer).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace lfm {
@@ -100,22 +101,10 @@ struct GnApplyArgs {
     float* copy_out;            // nullptr or fp32 [B, HW, C]
     __nv_bfloat16* raw_out;     // nullptr or bf16 [B, HW, C]
 };
-template <int J>
-__global__ void __launch_bounds__(256, 4)  // 4 blocks per SM resident: the host sizes the grid to ONE wave of 4 x SMs blocks
-gn_apply_kernel(GnApplyArgs a) {
-    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
-    pdl_trigger();
-    extern __shared__ float s_coef[];  // [2][C]: y = x * A[c] + Bc[c]   (GroupNorm affine and FiLM folded per channel)
-    __shared__ float s_mean[32], s_rstd[32];
-    constexpr int C = J * 128, cpg = C / 32;
-    // Eight 16-byte loads per lane are issued before the first store (one pixel of C <= 256 channels is only 1-2 loads per lane:
-    // a warp with a single 512-byte request in flight leaves the kernel latency-bound at ~40 % of the HBM rate), so a warp
-    // takes PIXB consecutive pixels per iteration.
-    constexpr int NL = J <= 4 ? 8 : 4;  // wide channel counts only occur on the small grids; 4 keeps them inside 64 registers
-    constexpr int JB = J >= NL ? NL : J;
-    constexpr int PIXB = J >= NL ? 1 : NL / J;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y;
+// Per-channel coefficients of one sample: y = x * A[c] + Bc[c] (GroupNorm affine and FiLM folded), into s_coef[2][C].
+template <int C>
+LFM_DEVICE void gn_coefficients(const GnApplyArgs& a, int b, float* s_coef, float* s_mean, float* s_rstd) {
+    constexpr int cpg = C / 32;
     if (threadIdx.x < 32) {
         double S = 0.0, Q = 0.0;
         if (a.bins != nullptr) {  // statistics accumulated by the producing convolution's epilogue (integer, order-free)
@@ -155,6 +144,27 @@ gn_apply_kernel(GnApplyArgs a) {
         s_coef[C + c] = Bc;
     }
     __syncthreads();
+}
+
+// pixels a warp takes per iteration: eight 16-byte loads per lane are issued before the first store (one pixel of C <= 256
+// channels is only 1-2 loads per lane: a warp with a single 512-byte request in flight leaves the kernel latency-bound at
+// ~40 % of the HBM rate).  Wide channel counts only occur on the small grids; 4 loads keep them inside 64 registers.
+__host__ __device__ constexpr int gn_apply_loads(int J) { return J <= 4 ? 8 : 4; }
+__host__ __device__ constexpr int gn_apply_pixels(int J) { return J >= gn_apply_loads(J) ? 1 : gn_apply_loads(J) / J; }
+template <int J>
+__global__ void __launch_bounds__(256, 4)  // 4 blocks per SM resident: the host sizes the grid to ONE wave of 4 x SMs blocks
+gn_apply_kernel(GnApplyArgs a) {
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
+    extern __shared__ float s_coef[];  // [2][C]
+    __shared__ float s_mean[32], s_rstd[32];
+    constexpr int C = J * 128;
+    constexpr int NL = gn_apply_loads(J);
+    constexpr int JB = J >= NL ? NL : J;
+    constexpr int PIXB = gn_apply_pixels(J);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    gn_coefficients<C>(a, b, s_coef, s_mean, s_rstd);
     const bool act = a.act != 0;
     for (int p0 = (blockIdx.x * 8 + warp) * PIXB; p0 < a.HW; p0 += gridDim.x * 8 * PIXB) {
         const size_t pix0 = static_cast<size_t>(b) * a.HW + p0;
@@ -166,9 +176,8 @@ gn_apply_kernel(GnApplyArgs a) {
 #pragma unroll
                 for (int u = 0; u < JB; ++u)
                     if (j0 + u < J && p0 + q < a.HW) {
-                        const size_t off = (pix0 + q) * C + 128 * (j0 + u) + 4 * lane;
                         if (a.src_bf16 != nullptr) {
-                            const uint2 r = *reinterpret_cast<const uint2*>(a.src_bf16 + off);
+                            const uint2 r = *reinterpret_cast<const uint2*>(a.src_bf16 + (pix0 + q) * C + 128 * (j0 + u) + 4 * lane);
                             const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
                             const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
                             vv[q][u] = make_float4(lo.x, lo.y, hi.x, hi.y);
@@ -198,6 +207,60 @@ gn_apply_kernel(GnApplyArgs a) {
                         }
                     }
                 }
+            }
+        }
+    }
+}
+
+// The same pass for a bf16 SOURCE of C <= 512 channels (conv1's output H1; no pass-through copies): 8-byte loads per lane kept
+// only half the bytes in flight and ran at 3.6 TB/s where the fp32-source pass reaches 5.5.  Here a warp takes a GROUP of PIXB
+// consecutive pixels as one contiguous run of 16-byte chunks (8 channels each; chunk t of the group belongs to lane t % 32), eight
+// (six for C = 384) chunks per lane in flight.  HW % PIXB == 0 (checked by the host).
+__host__ __device__ constexpr int gn_apply_bf16_pixels(int J) { return J == 1 ? 16 : J == 2 ? 8 : 4; }
+template <int J>
+__global__ void __launch_bounds__(256, 4)
+gn_apply_bf16_kernel(GnApplyArgs a) {
+    static_assert(J >= 1 && J <= 4, "C <= 512");
+    pdl_wait();  // PDL: nothing of the previous kernel's output is touched above this line
+    pdl_trigger();
+    extern __shared__ float s_coef[];  // [2][C]
+    __shared__ float s_mean[32], s_rstd[32];
+    constexpr int C = J * 128;
+    constexpr int PIXB = gn_apply_bf16_pixels(J);
+    constexpr int NCH = PIXB * J / 2;  // 16-byte chunks per lane per group: 8, 8, 6, 8
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    gn_coefficients<C>(a, b, s_coef, s_mean, s_rstd);
+    const bool act = a.act != 0;
+    for (int p0 = (blockIdx.x * 8 + warp) * PIXB; p0 < a.HW; p0 += gridDim.x * 8 * PIXB) {
+        const size_t base = (static_cast<size_t>(b) * a.HW + p0) * C;
+        uint4 raw[NCH];
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) raw[i] = *reinterpret_cast<const uint4*>(a.src_bf16 + base + (i * 32 + lane) * 8);
+        // chunk i of a lane covers channels (256 i + 8 lane) % C: NSETS different coefficient vectors per lane; take the chunks set
+        // by set so that only ONE set (16 registers) is live (the compiler otherwise hoists every set above the loop and spills)
+        constexpr int NSETS = J == 4 ? 2 : J == 3 ? 3 : 1;
+#pragma unroll
+        for (int set = 0; set < NSETS; ++set) {
+            if (set > 0) asm volatile("" ::: "memory");
+            const int ch = (set * 256 + lane * 8) % C;
+            const float4 A0 = *reinterpret_cast<const float4*>(s_coef + ch), A1 = *reinterpret_cast<const float4*>(s_coef + ch + 4);
+            const float4 B0 = *reinterpret_cast<const float4*>(s_coef + C + ch), B1 = *reinterpret_cast<const float4*>(s_coef + C + ch + 4);
+#pragma unroll
+            for (int i = set; i < NCH; i += NSETS) {
+                const int e = (i * 32 + lane) * 8;  // element offset inside the group
+                const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[i].x));
+                const float2 v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[i].y));
+                const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[i].z));
+                const float2 v3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[i].w));
+                float y0 = fmaf(v0.x, A0.x, B0.x), y1 = fmaf(v0.y, A0.y, B0.y), y2 = fmaf(v1.x, A0.z, B0.z), y3 = fmaf(v1.y, A0.w, B0.w);
+                float y4 = fmaf(v2.x, A1.x, B1.x), y5 = fmaf(v2.y, A1.y, B1.y), y6 = fmaf(v3.x, A1.z, B1.z), y7 = fmaf(v3.y, A1.w, B1.w);
+                if (act) {
+                    y0 = silu_fast(y0), y1 = silu_fast(y1), y2 = silu_fast(y2), y3 = silu_fast(y3);
+                    y4 = silu_fast(y4), y5 = silu_fast(y5), y6 = silu_fast(y6), y7 = silu_fast(y7);
+                }
+                *reinterpret_cast<uint4*>(a.out + base + e) =
+                    make_uint4(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7));
             }
         }
     }
