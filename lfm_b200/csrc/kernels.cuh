@@ -132,8 +132,12 @@ patch_embed_kernel(const float* __restrict__ x, int x_rows, const float* __restr
 // shared-memory ring filled by 1-D bulk async copies (cp.async.bulk + mbarrier transaction bytes), 8 rows per
 // stage, so loads of later rows are always in flight while the 8 warps normalise the current ones.
 // One warp per row, two-pass statistics in registers, coalesced bf16 stores.
-constexpr int kLnRows = 8;    // rows per stage (= warps per block)
-constexpr int kLnStages = 4;
+// 16 warps, one row each per stage: the per-row chain (shared-memory reads -> two warp reductions -> rsqrt -> modulate -> store, ~1500
+// clk with its waits) is latency-bound, and with 8 warps the kernel took 19 us whether x came from HBM or from L2
+// (tests/tools/l2_residency.cu: 21.4 us after plain stores, 24.6 us after a flush, event-timed).
+// Two shapes are kept for A/B runs (LFM_LN_ROWS = 8 | 16): 8 rows x 4 stages with per-warp modulation loads (round 1), and 16 rows x 3
+// stages with the tile's shift / scale vectors staged next to its rows.
+__host__ __device__ constexpr int ln_stages(int NV, int ROWS) { return ROWS == 8 ? 4 : (NV > 8 ? 2 : 3); }  // 16 rows: 3 x 72 KB at D = 1024
 
 LFM_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -149,15 +153,20 @@ LFM_DEVICE void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t byt
                  : "memory");
 }
 
-template <int NV>  // NV = D / 128 float4 per lane
-__global__ void __launch_bounds__(256, 1)
+template <int NV, int kLnRows>  // NV = D / 128 float4 per lane; kLnRows = rows per stage = warps per block
+__global__ void __launch_bounds__(kLnRows * 32, 1)
 ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ shift,
                    const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M, int order_flags) {
     constexpr int D = NV * 128;
+    constexpr int kLnStages = ln_stages(NV, kLnRows);
     const int order = order_flags & 3;          // tile order (below)
     const bool keep = (order_flags & 4) != 0;   // x is the residual stream: load with the evict_last L2 policy
     const uint64_t policy = keep ? l2_policy_evict_last() : 0;
-    constexpr uint32_t kStageBytes = kLnRows * D * 4;
+    // a stage = kLnRows rows of x + the shift and scale vectors of the tile's sample.  (Every warp used to fetch its own copy of
+    // the two vectors from L2 - 8 KB per 4 KB row, 134 MB per launch on top of the 67 MB of x: the pass was bound by L2 -> SM
+    // bandwidth at 19 us whether x sat in L2 or in HBM; tests/tools/l2_residency.cu.)
+    constexpr uint32_t kStageBytes = (kLnRows + (kLnRows == 16 ? 2 : 0)) * D * 4;
+    const bool mod_smem = kLnRows == 16 && rows_per_sample % kLnRows == 0;  // a tile never straddles two samples
     extern __shared__ __align__(128) uint8_t ln_smem[];
     __shared__ __align__(8) uint64_t full_bar[kLnStages];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,7 +197,13 @@ ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, c
         const int rows = min(kLnRows, M - tile * kLnRows);
         const uint32_t bytes = static_cast<uint32_t>(rows) * D * 4;
         uint64_t* bar = &full_bar[i % kLnStages];
-        mbar_arrive_expect_tx(bar, bytes);
+        mbar_arrive_expect_tx(bar, bytes + (mod_smem ? 2u * D * 4 : 0u));
+        if (mod_smem) {
+            const size_t boff = static_cast<size_t>(tile * kLnRows / rows_per_sample) * mod_stride;
+            uint8_t* dst = ln_smem + (i % kLnStages) * kStageBytes + kLnRows * D * 4;
+            bulk_load_1d(dst, shift + boff, D * 4, bar);
+            bulk_load_1d(dst + D * 4, scale + boff, D * 4, bar);
+        }
         if (keep)
             bulk_load_1d_hint(ln_smem + (i % kLnStages) * kStageBytes, x + static_cast<size_t>(tile) * kLnRows * D, bytes, bar, policy);
         else
@@ -202,16 +217,16 @@ ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, c
         const uint32_t parity = (i / kLnStages) & 1;
         const int row = tile_of(i) * kLnRows + warp;
         const bool ok = row < M;
-        // modulation vectors first: their L2 latency overlaps the wait for the row data
-        float4 sh[NV], sc[NV];
-        if (ok) {
+        // 8-row shape: the modulation vectors come from global memory, requested first so that their latency overlaps the wait
+        float4 shr[kLnRows == 8 ? NV : 1], scr[kLnRows == 8 ? NV : 1];
+        if (kLnRows == 8 && ok) {
             const size_t boff = static_cast<size_t>(row / rows_per_sample) * mod_stride;
             const float4* shp = reinterpret_cast<const float4*>(shift + boff);
             const float4* scp = reinterpret_cast<const float4*>(scale + boff);
 #pragma unroll
-            for (int m = 0; m < NV; ++m) {
-                sh[m] = __ldg(shp + m * 32 + lane);
-                sc[m] = __ldg(scp + m * 32 + lane);
+            for (int m = 0; m < (kLnRows == 8 ? NV : 0); ++m) {
+                shr[m] = __ldg(shp + m * 32 + lane);
+                scr[m] = __ldg(scp + m * 32 + lane);
             }
         }
         mbar_wait(&full_bar[stage], parity);
@@ -233,12 +248,23 @@ ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, c
             }
             const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + 1e-6f);
             uint2* yp = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+            const float4* shs = reinterpret_cast<const float4*>(ln_smem + stage * kStageBytes + kLnRows * D * 4);
+            const size_t boff = static_cast<size_t>(row / rows_per_sample) * mod_stride;
+            const float4* shg = reinterpret_cast<const float4*>(shift + boff);
+            const float4* scg = reinterpret_cast<const float4*>(scale + boff);
 #pragma unroll
             for (int m = 0; m < NV; ++m) {
-                const float a = fmaf((v[m].x - mean) * rstd, 1.f + sc[m].x, sh[m].x);
-                const float b = fmaf((v[m].y - mean) * rstd, 1.f + sc[m].y, sh[m].y);
-                const float c = fmaf((v[m].z - mean) * rstd, 1.f + sc[m].z, sh[m].z);
-                const float d = fmaf((v[m].w - mean) * rstd, 1.f + sc[m].w, sh[m].w);
+                float4 sh, sc;
+                if constexpr (kLnRows == 8) {
+                    sh = shr[m], sc = scr[m];
+                } else {
+                    sh = mod_smem ? shs[m * 32 + lane] : __ldg(shg + m * 32 + lane);
+                    sc = mod_smem ? shs[D / 4 + m * 32 + lane] : __ldg(scg + m * 32 + lane);
+                }
+                const float a = fmaf((v[m].x - mean) * rstd, 1.f + sc.x, sh.x);
+                const float b = fmaf((v[m].y - mean) * rstd, 1.f + sc.y, sh.y);
+                const float c = fmaf((v[m].z - mean) * rstd, 1.f + sc.z, sh.z);
+                const float d = fmaf((v[m].w - mean) * rstd, 1.f + sc.w, sh.w);
                 yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
             }
         }
