@@ -273,6 +273,51 @@ ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, c
     }
 }
 
+// The same pass without the shared-memory ring (LFM_LN_ROWS=0): one row per warp straight from global memory into registers, 64
+// registers so that 32 warps are resident per SM (8 independent row chains per scheduler instead of 4), the grid sweeping M in
+// order (upwards, or downwards for order 2).  Same arithmetic in the same order as ln_modulate_kernel: identical results.
+template <int NV>
+__global__ void __launch_bounds__(256, 4)
+ln_modulate_direct_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ shift,
+                          const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M, int order_flags) {
+    constexpr int D = NV * 128;
+    pdl_wait();
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool down = (order_flags & 3) == 2;
+    for (int r = blockIdx.x * 8 + warp; r < M; r += gridDim.x * 8) {
+        const int row = down ? M - 1 - r : r;
+        const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+        float4 v[NV];
+#pragma unroll
+        for (int m = 0; m < NV; ++m) v[m] = xp[m * 32 + lane];
+        float s = 0.f;
+#pragma unroll
+        for (int m = 0; m < NV; ++m) s += (v[m].x + v[m].y) + (v[m].z + v[m].w);
+        const float mean = warp_sum(s) / static_cast<float>(D);
+        float ss = 0.f;
+#pragma unroll
+        for (int m = 0; m < NV; ++m) {
+            const float a = v[m].x - mean, b = v[m].y - mean, c = v[m].z - mean, d = v[m].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + 1e-6f);
+        const size_t boff = static_cast<size_t>(row / rows_per_sample) * mod_stride;
+        const float4* shp = reinterpret_cast<const float4*>(shift + boff);
+        const float4* scp = reinterpret_cast<const float4*>(scale + boff);
+        uint2* yp = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+#pragma unroll
+        for (int m = 0; m < NV; ++m) {
+            const float4 sh = __ldg(shp + m * 32 + lane), sc = __ldg(scp + m * 32 + lane);
+            const float a = fmaf((v[m].x - mean) * rstd, 1.f + sc.x, sh.x);
+            const float b = fmaf((v[m].y - mean) * rstd, 1.f + sc.y, sh.y);
+            const float c = fmaf((v[m].z - mean) * rstd, 1.f + sc.z, sh.z);
+            const float d = fmaf((v[m].w - mean) * rstd, 1.f + sc.w, sh.w);
+            yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K11: FinalLayer (LN + modulate + Linear(D, p*p*C)) + unpatchify, fp32 (reference models/DiT.py:134-149,230-243).
 // Out-feature order of the linear is (p, q, c) -> pixel (c, 2h+p, 2w+q).  One warp per token; the 16 x D weight

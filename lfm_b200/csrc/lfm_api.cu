@@ -343,6 +343,10 @@ static cudaError_t launch_ln_inst(cudaStream_t s, const float* x, __nv_bfloat16*
                                   int mod_stride, int rows_per_sample, int M, int order) {
     static const int rows = env_int("LFM_LN_ROWS", 16);  // same-box A/B (r2w): 116.99 / 116.72 img/s vs 116.33 / 116.34 with 8
     if (rows == 16) return launch_ln_inst2<NV, 16>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
+    if (rows == 0) {
+        const int blocks = std::min((M + 7) / 8, 4 * g_num_sms);
+        return launch_k(ln_modulate_direct_kernel<NV>, dim3(blocks), 256, 0, s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
+    }
     return launch_ln_inst2<NV, 8>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
 }
 static cudaError_t launch_ln(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
