@@ -676,4 +676,146 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// DiT geometries other than (patch 2, 32 x 32 latents): patch sizes 4 / 8 and latent sides that give 16, 64 or 256 tokens
+// (reference models/DiT.py:355-415 - the /4 and /8 entries of DiT_models; img_resolution = image_size // f).  Both ends of
+// the network are < 0.1 % of its work, so these are plain kernels; the patch-2 / 32 x 32 presets keep the specialised ones.
+//
+// Patch embed for any p: patch vector (c, p, q) of P = C p^2 floats (timm PatchEmbed conv weight [D, C, p, p]), 8 tokens per block.
+__global__ void __launch_bounds__(256)
+patch_embed_generic_kernel(const float* __restrict__ x, int x_rows, const float* __restrict__ Wt /*[P, D]*/,
+                           const float* __restrict__ bias, const float* __restrict__ pos /*[T, D]*/, float* __restrict__ tok,
+                           int D, int G, int C, int p, int M) {
+    extern __shared__ float patch_sm[];  // [8][P]
+    const int P = C * p * p, T = G * G, HW = p * G;
+    const int m0 = blockIdx.x * 8;
+    for (int i = threadIdx.x; i < 8 * P; i += 256) {
+        const int tk = i / P, e = i % P;
+        const int m = m0 + tk;
+        float v = 0.f;
+        if (m < M) {
+            const int b = (m / T) % x_rows, t = m % T;
+            const int gh = t / G, gw = t % G;
+            const int c = e / (p * p), pp = (e / p) % p, q = e % p;
+            v = x[((static_cast<size_t>(b) * C + c) * HW + (p * gh + pp)) * HW + p * gw + q];
+        }
+        patch_sm[i] = v;
+    }
+    __syncthreads();
+    for (int d4 = threadIdx.x; d4 < D / 4; d4 += 256) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + d4);
+        float4 acc[8];
+#pragma unroll
+        for (int tk = 0; tk < 8; ++tk) acc[tk] = b4;
+        for (int e = 0; e < P; ++e) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(Wt + static_cast<size_t>(e) * D) + d4);
+#pragma unroll
+            for (int tk = 0; tk < 8; ++tk) {
+                const float pe = patch_sm[tk * P + e];
+                acc[tk].x = fmaf(w4.x, pe, acc[tk].x);
+                acc[tk].y = fmaf(w4.y, pe, acc[tk].y);
+                acc[tk].z = fmaf(w4.z, pe, acc[tk].z);
+                acc[tk].w = fmaf(w4.w, pe, acc[tk].w);
+            }
+        }
+#pragma unroll
+        for (int tk = 0; tk < 8; ++tk) {
+            const int m = m0 + tk;
+            if (m < M) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(m % T) * D) + d4);
+                reinterpret_cast<float4*>(tok + static_cast<size_t>(m) * D)[d4] =
+                    make_float4(acc[tk].x + p4.x, acc[tk].y + p4.y, acc[tk].z + p4.z, acc[tk].w + p4.w);
+            }
+        }
+    }
+}
+
+// FinalLayer + unpatchify for any p: LN + modulate in registers (one warp per token), then the P_out = p p C dot products
+// against the weight rows read through L2; out-feature j = (pp p + q) C + c  ->  pixel (c, p gh + pp, p gw + q).
+__global__ void __launch_bounds__(256)
+final_layer_generic_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
+                           int mod_stride, const float* __restrict__ W /*[P_out, D]*/, const float* __restrict__ bias,
+                           float* __restrict__ v_net, int M, int D, int G, int C, int p) {
+    constexpr int MAXV = 12;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nv = D / 128, T = G * G, HW = p * G, Pout = p * p * C;
+    for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+        const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+        float4 v[MAXV];
+        float s = 0.f;
+#pragma unroll
+        for (int m = 0; m < MAXV; ++m)
+            if (m < nv) {
+                v[m] = xp[m * 32 + lane];
+                s += (v[m].x + v[m].y) + (v[m].z + v[m].w);
+            }
+        const float mean = warp_sum(s) / static_cast<float>(D);
+        float ss = 0.f;
+#pragma unroll
+        for (int m = 0; m < MAXV; ++m)
+            if (m < nv) {
+                const float a = v[m].x - mean, b = v[m].y - mean, c = v[m].z - mean, d = v[m].w - mean;
+                ss += (a * a + b * b) + (c * c + d * d);
+            }
+        const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + 1e-6f);
+        const int bidx = row / T, t = row % T;
+        const size_t boff = static_cast<size_t>(bidx) * mod_stride;
+        const float4* shp = reinterpret_cast<const float4*>(shift + boff);
+        const float4* scp = reinterpret_cast<const float4*>(scale + boff);
+#pragma unroll
+        for (int m = 0; m < MAXV; ++m)
+            if (m < nv) {
+                const float4 sh = __ldg(shp + m * 32 + lane), sc = __ldg(scp + m * 32 + lane);
+                v[m].x = fmaf((v[m].x - mean) * rstd, 1.f + sc.x, sh.x);
+                v[m].y = fmaf((v[m].y - mean) * rstd, 1.f + sc.y, sh.y);
+                v[m].z = fmaf((v[m].z - mean) * rstd, 1.f + sc.z, sh.z);
+                v[m].w = fmaf((v[m].w - mean) * rstd, 1.f + sc.w, sh.w);
+            }
+        const int gh = t / G, gw = t % G;
+        for (int j0 = 0; j0 < Pout; j0 += 32) {
+            float mine = 0.f;
+            for (int jj = 0; jj < 32 && j0 + jj < Pout; ++jj) {
+                const float4* wp = reinterpret_cast<const float4*>(W + static_cast<size_t>(j0 + jj) * D);
+                float acc = 0.f;
+#pragma unroll
+                for (int m = 0; m < MAXV; ++m)
+                    if (m < nv) {
+                        const float4 w4 = __ldg(wp + m * 32 + lane);
+                        acc = fmaf(w4.x, v[m].x, acc);
+                        acc = fmaf(w4.y, v[m].y, acc);
+                        acc = fmaf(w4.z, v[m].z, acc);
+                        acc = fmaf(w4.w, v[m].w, acc);
+                    }
+                acc = warp_sum(acc);
+                if (lane == jj) mine = acc;
+            }
+            const int j = j0 + lane;
+            if (j < Pout) {
+                const int pp = j / (p * C), q = (j / C) % p, c = j % C;
+                v_net[((static_cast<size_t>(bidx) * C + c) * HW + (p * gh + pp)) * HW + p * gw + q] = mine + bias[j];
+            }
+        }
+    }
+}
+
+// qkv rows of timm's Attention (out-feature = which * D + head * dh + d, models/DiT.py:120 / SURVEY D6) re-ordered ONCE at upload
+// into the head-major layout (head * 3 dh + which * dh + d) that the short-sequence kernel attention_mma_kernel reads
+// (used when the token grid is 4 x 4 or 8 x 8).
+LFM_DEVICE int dit_qkv_src_row(int r, int D, int dh) {
+    const int h = r / (3 * dh), which = (r % (3 * dh)) / dh, d = r % dh;
+    return which * D + h * dh + d;
+}
+__global__ void dit_qkv_weight_repack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int D, int dh) {
+    const size_t n = static_cast<size_t>(3) * D * D;
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = static_cast<int>(i / D), k = static_cast<int>(i % D);
+    out[i] = __float2bfloat16(w[static_cast<size_t>(dit_qkv_src_row(r, D, dh)) * D + k]);
+}
+__global__ void dit_qkv_bias_repack_kernel(const float* __restrict__ b, float* __restrict__ out, int D, int dh) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= 3 * D) return;
+    out[r] = b[dit_qkv_src_row(r, D, dh)];
+}
+
 }  // namespace lfm

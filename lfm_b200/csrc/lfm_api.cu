@@ -388,7 +388,8 @@ struct ParamSlot {
     bool to_bf16 = false;
     int kind = 0;  // 0 copy fp32, 1 cast bf16, 2 conv [Co,Ci,kh,kw] -> bf16 [Co,kh,kw,Ci], 3 out-conv -> fp32 [4][9][C],
                    // 4 fp32 transpose [R, rest] -> [rest, R], 5 / 6 EDM qkv weight / bias row re-order (aux0 = head dim,
-                   // aux1 = target layout), 7 constant resample_filter (validated, not stored)
+                   // aux1 = target layout), 7 constant resample_filter (validated, not stored), 8 / 9 DiT qkv weight / bias rows
+                   // re-ordered head-major for the short-sequence attention kernel (aux0 = head dim)
     int aux0 = 0, aux1 = 0;
     bool set = false;
 };
@@ -506,9 +507,16 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     lfm_ctx* ctx = nullptr;
     if (desc == nullptr || out == nullptr) return fail(nullptr, "lfm_create: null argument");
     if (desc->arch != LFM_ARCH_DIT) return fail(nullptr, "lfm_create: unsupported arch %d", desc->arch);
-    if (desc->patch_size != 2) return fail(nullptr, "lfm_create: only patch_size 2 is implemented (got %d)", desc->patch_size);
-    if (desc->img_resolution != 32)
-        return fail(nullptr, "lfm_create: only 32x32 latents (256 tokens) are implemented (got %d)", desc->img_resolution);
+    // Geometries (models/DiT.py:355-415; img_resolution = image_size // f): patch 2 / 4 / 8 on latents whose token grid is
+    // 4 x 4, 8 x 8 or 16 x 16 - e.g. /2 on 32 x 32 (every released preset), /4 on 64 x 64 or 32 x 32, /8 on 32 x 32.
+    if (desc->patch_size != 2 && desc->patch_size != 4 && desc->patch_size != 8)
+        return fail(nullptr, "lfm_create: patch_size must be 2, 4 or 8 (got %d)", desc->patch_size);
+    {
+        const int g = desc->img_resolution / desc->patch_size;
+        if (desc->img_resolution <= 0 || desc->img_resolution % desc->patch_size != 0 || !(g == 4 || g == 8 || g == 16))
+            return fail(nullptr, "lfm_create: the token grid (img_resolution / patch_size) must be 4, 8 or 16 per side, i.e. 16, 64 or "
+                        "256 tokens (got img_resolution %d, patch_size %d)", desc->img_resolution, desc->patch_size);
+    }
     {
         const int nv = desc->hidden_size / 128;
         if (desc->hidden_size % 128 != 0 || !(nv == 2 || nv == 3 || nv == 6 || nv == 8 || nv == 9))
@@ -545,29 +553,33 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     ctx->l2_hint = env_int("LFM_L2_HINT", 0);
     ctx->ln_fuse = env_int("LFM_LN_FUSE", 0);  // measured (r2b): the in-kernel LayerNorm finisher is 2.6x SLOWER end to end - off
     const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
+    const int ps = desc->patch_size;
+    const int P = ctx->C * ps * ps;  // elements of one patch = out-features of the final linear
+    // 4 x 4 / 8 x 8 token grids run attention on the short-sequence mma.sync kernel, which reads head-major qkv rows
+    const bool qkv_head_major = T != 256;
 
     if (dev_alloc(ctx, &ctx->pos, (size_t)T * D)) return 1;
-    if (dev_alloc(ctx, &ctx->pe_w, (size_t)D * 16)) return 1;
+    if (dev_alloc(ctx, &ctx->pe_w, (size_t)D * P)) return 1;
     if (dev_alloc(ctx, &ctx->pe_b, D)) return 1;
     if (dev_alloc(ctx, &ctx->t_w0, (size_t)D * 256)) return 1;
     if (dev_alloc(ctx, &ctx->t_b0, D)) return 1;
     if (dev_alloc(ctx, &ctx->t_w2, (size_t)D * D)) return 1;
     if (dev_alloc(ctx, &ctx->t_b2, D)) return 1;
     if (dev_alloc(ctx, &ctx->ytable, (size_t)desc->table_rows * D)) return 1;
-    if (dev_alloc(ctx, &ctx->fin_w, (size_t)16 * D)) return 1;
-    if (dev_alloc(ctx, &ctx->fin_b, 16)) return 1;
+    if (dev_alloc(ctx, &ctx->fin_w, (size_t)P * D)) return 1;
+    if (dev_alloc(ctx, &ctx->fin_b, P)) return 1;
     if (dev_alloc(ctx, &ctx->w_mod, (size_t)ctx->Nmod * D)) return 1;
     if (dev_alloc(ctx, &ctx->b_mod, ctx->Nmod)) return 1;
     add_param(ctx, "pos_embed", ctx->pos, {1, T, D}, false);
-    add_param_kind(ctx, "x_embedder.proj.weight", ctx->pe_w, {D, 4, 2, 2}, 4);  // stored transposed [16, D]
+    add_param_kind(ctx, "x_embedder.proj.weight", ctx->pe_w, {D, 4, ps, ps}, 4);  // stored transposed [P, D]
     add_param(ctx, "x_embedder.proj.bias", ctx->pe_b, {D}, false);
     add_param(ctx, "t_embedder.mlp.0.weight", ctx->t_w0, {D, 256}, false);
     add_param(ctx, "t_embedder.mlp.0.bias", ctx->t_b0, {D}, false);
     add_param(ctx, "t_embedder.mlp.2.weight", ctx->t_w2, {D, D}, false);
     add_param(ctx, "t_embedder.mlp.2.bias", ctx->t_b2, {D}, false);
     add_param(ctx, "y_embedder.embedding_table.weight", ctx->ytable, {desc->table_rows, D}, false);
-    add_param(ctx, "final_layer.linear.weight", ctx->fin_w, {16, D}, false);
-    add_param(ctx, "final_layer.linear.bias", ctx->fin_b, {16}, false);
+    add_param(ctx, "final_layer.linear.weight", ctx->fin_w, {P, D}, false);
+    add_param(ctx, "final_layer.linear.bias", ctx->fin_b, {P}, false);
     add_param(ctx, "final_layer.adaLN_modulation.1.weight", ctx->w_mod + (size_t)6 * L * D * D, {2 * D, D}, true);
     add_param(ctx, "final_layer.adaLN_modulation.1.bias", ctx->b_mod + (size_t)6 * L * D, {2 * D}, false);
     ctx->blk.resize(L);
@@ -582,8 +594,13 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
         if (dev_alloc(ctx, &b.b_fc1, Hd)) return 1;
         if (dev_alloc(ctx, &b.b_fc2, D)) return 1;
         const std::string p = "blocks." + std::to_string(i) + ".";
-        add_param(ctx, p + "attn.qkv.weight", b.w_qkv, {3 * D, D}, true);
-        add_param(ctx, p + "attn.qkv.bias", b.b_qkv, {3 * D}, false);
+        if (qkv_head_major) {
+            add_param_aux(ctx, p + "attn.qkv.weight", b.w_qkv, {3 * D, D}, 8, 64, 0);
+            add_param_aux(ctx, p + "attn.qkv.bias", b.b_qkv, {3 * D}, 9, 64, 0);
+        } else {
+            add_param(ctx, p + "attn.qkv.weight", b.w_qkv, {3 * D, D}, true);
+            add_param(ctx, p + "attn.qkv.bias", b.b_qkv, {3 * D}, false);
+        }
         add_param(ctx, p + "attn.proj.weight", b.w_proj, {D, D}, true);
         add_param(ctx, p + "attn.proj.bias", b.b_proj, {D}, false);
         add_param(ctx, p + "mlp.fc1.weight", b.w_fc1, {Hd, D}, true);
@@ -639,6 +656,12 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
         } else if (s.kind == 6) {
             edm_qkv_bias_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<float*>(s.dst),
                                                                     static_cast<int>(s.shape[0] / 3), s.aux0, s.aux1);
+        } else if (s.kind == 8) {
+            dit_qkv_weight_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst),
+                                                                      static_cast<int>(s.shape[1]), s.aux0);
+        } else if (s.kind == 9) {
+            dit_qkv_bias_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<float*>(s.dst),
+                                                                    static_cast<int>(s.shape[0] / 3), s.aux0);
         } else if (s.kind == 7) {
             float h[4] = {0.f, 0.f, 0.f, 0.f};
             CUDA_OK(cudaMemcpy(h, ctx->staging, sizeof(h), cudaMemcpyDeviceToHost));
@@ -805,8 +828,15 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         CUDA_OK(launch_gemm(s, ctx->tm_csilu, ctx->tm_wmod, crows, ctx->Nmod, D, EPI_BIAS_F32, ctx->bn_mod, ep));
         ctx->launches++;
     }
-    patch_embed_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, x_rows, ctx->pe_w, ctx->pe_b, ctx->pos, ctx->x_tok, D, ctx->G,
-                                                   ctx->C, M);
+    const int ps = ctx->d.patch_size;
+    if (ps == 2) {
+        patch_embed_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, x_rows, ctx->pe_w, ctx->pe_b, ctx->pos, ctx->x_tok, D, ctx->G,
+                                                       ctx->C, M);
+    } else {
+        const int smem = 8 * ctx->C * ps * ps * (int)sizeof(float);
+        patch_embed_generic_kernel<<<(M + 7) / 8, 256, smem, s>>>(x, x_rows, ctx->pe_w, ctx->pe_b, ctx->pos, ctx->x_tok, D,
+                                                                  ctx->G, ctx->C, ps, M);
+    }
     LAUNCH_OK();
     // L2 zig-zag (LFM_ZIGZAG): consecutive kernels sweep the token rows in opposite directions, so each starts on the
     // rows its producer wrote last (still L2-resident) instead of the rows that were evicted first.
@@ -839,7 +869,9 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         }
         {
             const int d = next_dir();
-            if (ctx->attn_variant >= 2)
+            if (T != 256)  // 4 x 4 / 8 x 8 token grids: warp-level mma.sync kernel on head-major qkv rows (see lfm_create)
+                CUDA_OK(launch_attention_mma(s, ctx->qkv, ctx->attn, T, 64, D, ctx->H, rows * ctx->H));
+            else if (ctx->attn_variant >= 2)
                 CUDA_OK(launch_attention2(s, ctx->tm_qkv_kv, ctx->tm_attn, rows, ctx->H, D, ctx->attn_variant, d));
             else if (ctx->attn_variant == 0)
                 CUDA_OK(launch_attention_inst<true>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
@@ -906,8 +938,12 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
         CUDA_OK(smem_opt_in(once, final_layer_kernel, 16 * 1536 * 4));  // largest supported width (hidden_size <= 1536)
         int grid = (M + 7) / 8;
         if (grid > 2 * g_num_sms) grid = 2 * g_num_sms;
-        final_layer_kernel<<<grid, 256, smem, s>>>(ctx->x_tok, mf, mf + D, Nmod, ctx->fin_w, ctx->fin_b, ctx->v_net, M, D,
-                                                   ctx->G, ctx->C);
+        if (ps == 2)
+            final_layer_kernel<<<grid, 256, smem, s>>>(ctx->x_tok, mf, mf + D, Nmod, ctx->fin_w, ctx->fin_b, ctx->v_net, M, D,
+                                                       ctx->G, ctx->C);
+        else
+            final_layer_generic_kernel<<<grid, 256, 0, s>>>(ctx->x_tok, mf, mf + D, Nmod, ctx->fin_w, ctx->fin_b, ctx->v_net, M,
+                                                            D, ctx->G, ctx->C, ps);
         LAUNCH_OK();
     }
     return 0;

@@ -47,6 +47,19 @@ CASES = {
     "mini_d384": (dict(depth=3, hidden_size=384, patch_size=2, num_heads=6, img_resolution=32, in_channels=4,
                        label_dropout=0.1, num_classes=5), 13),
 }
+# Other DiT geometries of the reference's size table (models/DiT.py:355-415: the /4 and /8 entries) and other latent sides
+# (img_resolution = image_size // f): token grids of 8 x 8, 4 x 4 and - with patch 4 on 64 x 64 latents - 16 x 16.
+# Written by `make_goldens.py patch` with its own generator, so the fixtures above stay byte-identical.
+GEOMETRY_CASES = {
+    "mini_p4": (dict(depth=2, hidden_size=256, patch_size=4, num_heads=4, img_resolution=32, in_channels=4,
+                     label_dropout=0.1, num_classes=10), 21),
+    "mini_p8": (dict(depth=2, hidden_size=384, patch_size=8, num_heads=6, img_resolution=32, in_channels=4,
+                     label_dropout=0.0, num_classes=1), 22),
+    "mini_r64p4": (dict(depth=2, hidden_size=256, patch_size=4, num_heads=4, img_resolution=64, in_channels=4,
+                        label_dropout=0.0, num_classes=1), 23),
+    "mini_r16p2": (dict(depth=2, hidden_size=256, patch_size=2, num_heads=4, img_resolution=16, in_channels=4,
+                        label_dropout=0.1, num_classes=5), 24),
+}
 FULL = {
     "dit_l2": ("DiT-L/2", dict(img_resolution=32, in_channels=4, label_dropout=0.0, num_classes=1), 1),
     "dit_b2": ("DiT-B/2", dict(img_resolution=32, in_channels=4, label_dropout=0.1, num_classes=1000), 1),
@@ -200,10 +213,46 @@ def make_edm_goldens(g):
         del net
 
 
+def make_geometry_goldens(models, ks, g):
+    """One evaluation (0-d t without labels, [B] t with labels, forward_with_cfg) and the reference's own Euler / Heun
+    samplers on the reference DiT for each entry of GEOMETRY_CASES."""
+    for name, (kw, seed) in GEOMETRY_CASES.items():
+        net, cfg = build(models, kw, seed)
+        B, S = 2, kw["img_resolution"]
+        x = torch.randn(B, 4, S, S, generator=g)
+        out = {"x": x, "weight_seed": np.int64(seed)}
+        for k, v in kw.items():
+            out["cfg_" + k] = np.float64(v)
+        out["t_scalar"] = torch.tensor(0.61)
+        out["v_scalar_ynone"] = net(out["t_scalar"], x)
+        tv = torch.tensor([0.85, 0.2])
+        y = torch.randint(0, kw["num_classes"], (B,), generator=g)
+        out["t_vec"], out["y"] = tv, y
+        out["v_vec_y"] = net(tv, x, y)
+        if kw["num_classes"] > 1:
+            x2 = torch.cat([x, x], 0)
+            y2 = torch.cat([y, torch.full((B,), kw["num_classes"])], 0)
+            out["y_cfg"] = y2
+            out["v_cfg_1p5"] = net.forward_with_cfg(torch.tensor([0.4] * (2 * B)), x2, y2, cfg_scale=1.5)
+            mk, xs = dict(y=y2, cfg_scale=1.5), x2
+        else:
+            mk, xs = {}, x
+        common = dict(model_kwargs=mk, device="cpu", clip_denoised=False, sigma_min=1e-5, sigma_max=1.0,
+                      s_tmin=0.0, s_tmax=1.0, s_churn=0.0)
+        out["euler6"] = ks.karras_sample(net, xs, steps=6, sampler="euler", **common)
+        out["heun5"] = ks.karras_sample(net, xs, steps=5, sampler="heun", **common)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
+        print("wrote", name, {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
     models, ks = _import_reference()
+    if sys.argv[1:] == ["patch"]:   # only the other-geometry DiT fixtures (own generator)
+        make_geometry_goldens(models, ks, torch.Generator().manual_seed(2468))
+        return
     if sys.argv[1:] == ["edm"]:     # only the DhariwalUNet fixtures (own generator: the others stay byte-identical)
         make_edm_goldens(torch.Generator().manual_seed(8765))
         return

@@ -118,7 +118,12 @@ def test_attention(dev, variant, B, H):
 # ------------------------------------------------------------------------------------------------ reference fixtures
 
 
-@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"])
+# patch 4 / 8 and other latent sides: token grids 8 x 8 / 4 x 4 (short-sequence attention kernel on head-major qkv rows, generic
+# patch-embed / final-layer kernels) and 16 x 16 with patch 4 on 64 x 64 latents (oracle/make_goldens.py patch)
+GEOMETRY = ["mini_p4", "mini_p8", "mini_r64p4", "mini_r16p2"]
+
+
+@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"] + GEOMETRY)
 def test_forward_vs_reference_fixture(dev, name):
     g = load_golden(name)
     cfg = cfg_from_golden(g)
@@ -139,7 +144,7 @@ def test_forward_vs_reference_fixture(dev, name):
             net(0.5, x, torch.tensor([0, cfg.num_classes + 5], device=dev))
 
 
-@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"])
+@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"] + GEOMETRY)
 def test_fixed_step_samplers_vs_reference_fixture(dev, name):
     g = load_golden(name)
     cfg = cfg_from_golden(g)

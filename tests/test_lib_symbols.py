@@ -58,6 +58,9 @@ def test_unsupported_shapes_are_rejected(lib):
     bad = _lib.ModelDesc(0, 32, 2, 4, 1152, 28, 16, 4608, 1)  # head_dim 72 (DiT-XL): not implemented
     assert lib.lfm_create(ctypes.byref(bad), 0, ctypes.byref(ctx)) != 0
     assert "head_dim" in _lib.last_error()
-    bad = _lib.ModelDesc(0, 32, 4, 4, 1024, 24, 16, 4096, 1)  # patch 4
+    bad = _lib.ModelDesc(0, 32, 3, 4, 1024, 24, 16, 4096, 1)  # patch 3 (the reference's table has 2, 4, 8)
     assert lib.lfm_create(ctypes.byref(bad), 0, ctypes.byref(ctx)) != 0
     assert "patch_size" in _lib.last_error()
+    bad = _lib.ModelDesc(0, 64, 2, 4, 1024, 24, 16, 4096, 1)  # 64 x 64 latents with patch 2: 1024 tokens, not implemented
+    assert lib.lfm_create(ctypes.byref(bad), 0, ctypes.byref(ctx)) != 0
+    assert "token grid" in _lib.last_error()

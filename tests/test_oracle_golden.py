@@ -15,7 +15,10 @@ from tests._util import T, cfg_from_golden, load_golden, oracle_model, rel_l2
 TOL = 2e-5
 
 
-@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"])
+GEOMETRY = ["mini_p4", "mini_p8", "mini_r64p4", "mini_r16p2"]   # patch 4 / 8 and other latent sides (make_goldens.py patch)
+
+
+@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"] + GEOMETRY)
 def test_forward_matches_reference(name):
     g = load_golden(name)
     cfg = cfg_from_golden(g)
@@ -28,7 +31,7 @@ def test_forward_matches_reference(name):
     assert float(np.abs(g["v_vec_y"]).mean()) > 1e-3  # synthetic init is non-degenerate
 
 
-@pytest.mark.parametrize("name", ["mini_cond", "mini_d384"])
+@pytest.mark.parametrize("name", ["mini_cond", "mini_d384", "mini_p4", "mini_r16p2"])
 def test_cfg_matches_reference(name):
     g = load_golden(name)
     cfg = cfg_from_golden(g)
@@ -40,7 +43,7 @@ def test_cfg_matches_reference(name):
     assert torch.equal(v[:2], v[2:])
 
 
-@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"])
+@pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"] + GEOMETRY)
 def test_fixed_step_samplers_match_reference(name):
     g = load_golden(name)
     cfg = cfg_from_golden(g)
