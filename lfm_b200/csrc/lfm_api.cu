@@ -162,16 +162,21 @@ template <int EPI>
 static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb,
                                      const CUtensorMap& tout, int M, int N, int K, const GemmEpi& ep,
                                      ConvGeom cg = ConvGeom{0, 0, 0, 0, 1}, const CUtensorMap* tbh = nullptr, int ksplit = 1,
-                                     int split_row_pitch = 0) {
+                                     int split_row_pitch = 0, bool starved_halves = false) {
     static DevOnce once;
     auto kern = gemm2_bf16_tcgen05<EPI>;
     if (cudaError_t e = smem_opt_in(once, kern, kG2SmemBytes)) return e;
     const int tiles = ((M + 255) / 256) * ((N + kG2BlockN - 1) / kG2BlockN) * ksplit;
     int clusters = g_num_sms / 2;
-    if (tiles < clusters) clusters = tiles;
     static const int split_env = env_int("LFM_GEMM_SPLIT", 1);
+    const bool can_split = tbh != nullptr && split_env != 0;
+    static const int halves_env = env_int("LFM_GEMM_HALVES", 1);  // A/B switch of the tile-starved mode below
+    if (starved_halves && halves_env && can_split && ksplit == 1 && 2 * tiles <= clusters)
+        clusters = 2 * tiles;  // tile-starved launch: one CTA pair per 256 x 128 half tile (the kernel sees 2 * tiles <= clusters)
+    else if (tiles < clusters)
+        clusters = tiles;
     return launch_k(kern, dim3(2 * clusters), kG2Threads, kG2SmemBytes, s, ta, tb, tout, tbh != nullptr ? *tbh : tb, M, N, K, ep, cg,
-                    (tbh != nullptr && split_env) ? 1 : 0, ksplit, split_row_pitch);
+                    can_split ? 1 : 0, ksplit, split_row_pitch);
 }
 
 // Pair kernel with the LayerNorm finisher (ep.ln_out != nullptr; N == D): see GemmEpi::rb_count
@@ -295,11 +300,11 @@ static cudaError_t launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUte
     if (block_n == kGemmPair) {
         if (tout == nullptr) return cudaErrorInvalidValue;
         const ConvGeom cg{0, 0, 0, 0, 1};
-        if (epi == EPI_BIAS_BF16) return launch_gemm2_inst<EPI_BIAS_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
-        if (epi == EPI_BIAS_GELU_BF16) return launch_gemm2_inst<EPI_BIAS_GELU_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
+        if (epi == EPI_BIAS_BF16) return launch_gemm2_inst<EPI_BIAS_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh, 1, 0, true);
+        if (epi == EPI_BIAS_GELU_BF16) return launch_gemm2_inst<EPI_BIAS_GELU_BF16>(s, ta, tb, *tout, M, N, K, ep, cg, tbh, 1, 0, true);
         if (epi == EPI_GATE_RESID_F32 && ep.fin_ctl != nullptr) return launch_gemm2_fin(s, ta, tb, *tout, M, N, K, ep, tbh);
-        if (epi == EPI_GATE_RESID_F32) return launch_gemm2_inst<EPI_GATE_RESID_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
-        if (epi == EPI_BIAS_F32) return launch_gemm2_inst<EPI_BIAS_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh);
+        if (epi == EPI_GATE_RESID_F32) return launch_gemm2_inst<EPI_GATE_RESID_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh, 1, 0, true);
+        if (epi == EPI_BIAS_F32) return launch_gemm2_inst<EPI_BIAS_F32>(s, ta, tb, *tout, M, N, K, ep, cg, tbh, 1, 0, true);
         return cudaErrorInvalidValue;
     }
 #define LFM_GEMM_CASE(BN, E) \

@@ -13,10 +13,13 @@ from lfm_b200.synthetic import synthetic_state_dict  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 mt = sys.argv[3] if len(sys.argv) > 3 else "DiT-L/2"
-FLOPS = {"DiT-L/2": 161386856448, "DiT-B/2": 46003912704}[mt]
 dev = torch.device("cuda:0")
 with torch.device("meta"):
     net = lfm_b200.DiT_models[mt](img_resolution=32, in_channels=4, label_dropout=0.0, num_classes=1)
+# algorithmic FLOPs per sample per evaluation: 161,386,856,448 for DiT-L/2, 46,003,912,704 for DiT-B/2
+L_, D_, P_ = net.depth, net.hidden_size, net.patch_size ** 2 * net.in_channels
+T_ = (net.img_resolution // net.patch_size) ** 2
+FLOPS = L_ * (24 * T_ * D_ * D_ + 4 * T_ * T_ * D_ + 12 * D_ * D_) + 2 * T_ * P_ * D_ + 2 * (256 * D_ + D_ * D_) + 4 * D_ * D_ + 2 * T_ * D_ * P_
 sd = synthetic_state_dict(net, 1)
 net = net.to_empty(device="cpu")
 net.load_state_dict(sd, strict=True)
