@@ -45,6 +45,10 @@ LFM_DEVICE float row_max128(const uint32_t (*v)[32]) {
     return fmaxf(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], fmax3(m[5], m[6], m[7])));
 }
 
+// X2 (LFM_ATTN_X2): the softmax / merge arithmetic in packed f32x2 instructions - per PAIR of scores one fma (scale, minus the row
+// maximum), two MUFU.EX2, one add into a packed partial sum and one bf16x2 conversion (5 issue slots instead of 7); same values, the
+// row sum is accumulated in a different (equally valid) order.
+template <bool X2>
 __global__ void __launch_bounds__(kA2Threads, 1)
 attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D] bf16, box {64, 256}
                     const __grid_constant__ CUtensorMap tmap_out,  // out [M, D]  bf16, box {64, 128}
@@ -177,19 +181,36 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
                 const float mx = row_max128(v);
                 mAs = mx * scale_log2e;
                 float sacc[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial sums: no serial FADD chain behind the MUFU pipe
+                uint64_t sacc2[4] = {0ull, 0ull, 0ull, 0ull};
+                const uint64_t sc2 = pk2(scale_log2e, scale_log2e), nm2 = pk2(-mAs, -mAs);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j]), scale_log2e, -mAs));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j + 1]), scale_log2e, -mAs));
-                        sacc[j & 3] += p0 + p1;
+                        float p0, p1;
+                        if constexpr (X2) {
+                            float a0, a1;
+                            upk2(fma2(pk2(__uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1])), sc2, nm2), a0, a1);
+                            p0 = ex2_approx(a0);
+                            p1 = ex2_approx(a1);
+                            sacc2[j & 3] = add2(sacc2[j & 3], pk2(p0, p1));
+                        } else {
+                            p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j]), scale_log2e, -mAs));
+                            p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j + 1]), scale_log2e, -mAs));
+                            sacc[j & 3] += p0 + p1;
+                        }
                         pk[j] = pack_bf16x2(p0, p1);
                     }
                     tmem_st_32x32b_x16(taddr + c * 16, pk);  // P_A -> cols [0,64) (S_A is already in registers)
                 }
-                sumA = (sacc[0] + sacc[1]) + (sacc[2] + sacc[3]);
+                if constexpr (X2) {
+                    float lo, hi;
+                    upk2(add2(add2(sacc2[0], sacc2[1]), add2(sacc2[2], sacc2[3])), lo, hi);
+                    sumA = lo + hi;
+                } else {
+                    sumA = (sacc[0] + sacc[1]) + (sacc[2] + sacc[3]);
+                }
             }
             {
                 uint32_t v[4][32];
@@ -202,19 +223,36 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
                 const float mx = row_max128(v);
                 mBs = mx * scale_log2e;
                 float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+                uint64_t sacc2[4] = {0ull, 0ull, 0ull, 0ull};
+                const uint64_t sc2 = pk2(scale_log2e, scale_log2e), nm2 = pk2(-mBs, -mBs);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j]), scale_log2e, -mBs));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j + 1]), scale_log2e, -mBs));
-                        sacc[j & 3] += p0 + p1;
+                        float p0, p1;
+                        if constexpr (X2) {
+                            float a0, a1;
+                            upk2(fma2(pk2(__uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1])), sc2, nm2), a0, a1);
+                            p0 = ex2_approx(a0);
+                            p1 = ex2_approx(a1);
+                            sacc2[j & 3] = add2(sacc2[j & 3], pk2(p0, p1));
+                        } else {
+                            p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j]), scale_log2e, -mBs));
+                            p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * j + 1]), scale_log2e, -mBs));
+                            sacc[j & 3] += p0 + p1;
+                        }
                         pk[j] = pack_bf16x2(p0, p1);
                     }
                     tmem_st_32x32b_x16(taddr + 64 + c * 16, pk);  // P_B -> cols [64,128)
                 }
-                sumB = (sacc[0] + sacc[1]) + (sacc[2] + sacc[3]);
+                if constexpr (X2) {
+                    float lo, hi;
+                    upk2(add2(add2(sacc2[0], sacc2[1]), add2(sacc2[2], sacc2[3])), lo, hi);
+                    sumB = lo + hi;
+                } else {
+                    sumB = (sacc[0] + sacc[1]) + (sacc[2] + sacc[3]);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
@@ -238,9 +276,18 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float o[8];
+                        if constexpr (X2) {
+                            const uint64_t wA2 = pk2(wA, wA), wB2 = pk2(wB, wB);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            o[e] = fmaf(wA, __uint_as_float(va[8 * j + e]), wB * __uint_as_float(vb[8 * j + e]));
+                            for (int e = 0; e < 8; e += 2)
+                                upk2(fma2(wA2, pk2(__uint_as_float(va[8 * j + e]), __uint_as_float(va[8 * j + e + 1])),
+                                          mul2(wB2, pk2(__uint_as_float(vb[8 * j + e]), __uint_as_float(vb[8 * j + e + 1])))),
+                                     o[e], o[e + 1]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                o[e] = fmaf(wA, __uint_as_float(va[8 * j + e]), wB * __uint_as_float(vb[8 * j + e]));
+                        }
                         uint4 u;
                         u.x = pack_bf16x2(o[0], o[1]);
                         u.y = pack_bf16x2(o[2], o[3]);

@@ -266,6 +266,28 @@ LFM_DEVICE void mul_x2(float& a, float& b, float c, float d) {  // (a, b) *= (c,
     asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x));
 }
+// packed-pair building blocks (one issue slot per pair of fp32 values)
+LFM_DEVICE uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+LFM_DEVICE void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+LFM_DEVICE uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+LFM_DEVICE uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+LFM_DEVICE uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 LFM_DEVICE float silu(float x) { return x / (1.0f + __expf(-x)); }
 // x * rcp.approx(1 + ex2.approx(..)): 5 instructions, 2 of them MUFU, relative error ~2 ulp of fp32 (the result is rounded to bf16).
 // The IEEE division above compiles to MUFU.RCP + Newton steps + FCHK + a slow-path call per element, which made the GroupNorm

@@ -153,7 +153,11 @@ LFM_DEVICE void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t byt
                  : "memory");
 }
 
-template <int NV, int kLnRows>  // NV = D / 128 float4 per lane; kLnRows = rows per stage = warps per block
+// X2 (LFM_LN_X2, 16-row shape): the row arithmetic in Blackwell's packed f32x2 instructions - the pass is bound by the length of each
+// warp's dependent instruction chain (407 warp instructions per row at ~37 % issue utilisation, profiles/r2y), and two thirds of
+// those are fp32 adds / multiplies / fmas that pair up: sum 32 -> 16, variance 64 -> 32, modulate 128 -> 64 issue slots per row.
+// y = (x - mean) * (rstd * (1 + scale)) + shift: the same value up to one rounding of the product.
+template <int NV, int kLnRows, bool X2 = false>  // NV = D / 128 float4 per lane; kLnRows = rows per stage = warps per block
 __global__ void __launch_bounds__(kLnRows * 32, 1)
 ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ shift,
                    const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M, int order_flags) {
@@ -230,6 +234,55 @@ ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, c
             }
         }
         mbar_wait(&full_bar[stage], parity);
+        if constexpr (X2) {
+            if (ok) {
+                const float4* xp = reinterpret_cast<const float4*>(ln_smem + stage * kStageBytes + warp * D * 4);
+                uint64_t pr[NV][2];
+                uint64_t acc = pk2(0.f, 0.f);
+#pragma unroll
+                for (int m = 0; m < NV; ++m) {
+                    const float4 t4 = xp[m * 32 + lane];
+                    pr[m][0] = pk2(t4.x, t4.y);
+                    pr[m][1] = pk2(t4.z, t4.w);
+                    acc = add2(acc, add2(pr[m][0], pr[m][1]));
+                }
+                float ax, ay;
+                upk2(acc, ax, ay);
+                const float mean = warp_sum(ax + ay) / static_cast<float>(D);
+                const uint64_t nmean = pk2(-mean, -mean);
+                uint64_t q0 = pk2(0.f, 0.f), q1 = pk2(0.f, 0.f);
+#pragma unroll
+                for (int m = 0; m < NV; ++m) {
+                    const uint64_t d0 = add2(pr[m][0], nmean), d1 = add2(pr[m][1], nmean);
+                    q0 = fma2(d0, d0, q0);
+                    q1 = fma2(d1, d1, q1);
+                }
+                float qx, qy;
+                upk2(add2(q0, q1), qx, qy);
+                const float rstd = rsqrtf(warp_sum(qx + qy) / static_cast<float>(D) + 1e-6f);
+                const uint64_t r2 = pk2(rstd, rstd), one2 = pk2(1.f, 1.f);
+                uint2* yp = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+                const float4* shs = reinterpret_cast<const float4*>(ln_smem + stage * kStageBytes + kLnRows * D * 4);
+                const size_t boff = static_cast<size_t>(row / rows_per_sample) * mod_stride;
+                const float4* shg = reinterpret_cast<const float4*>(shift + boff);
+                const float4* scg = reinterpret_cast<const float4*>(scale + boff);
+#pragma unroll
+                for (int m = 0; m < NV; ++m) {
+                    const float4 sh = mod_smem ? shs[m * 32 + lane] : __ldg(shg + m * 32 + lane);
+                    const float4 sc = mod_smem ? shs[D / 4 + m * 32 + lane] : __ldg(scg + m * 32 + lane);
+                    const uint64_t g0 = mul2(add2(pk2(sc.x, sc.y), one2), r2), g1 = mul2(add2(pk2(sc.z, sc.w), one2), r2);
+                    const uint64_t o0 = fma2(add2(pr[m][0], nmean), g0, pk2(sh.x, sh.y));
+                    const uint64_t o1 = fma2(add2(pr[m][1], nmean), g1, pk2(sh.z, sh.w));
+                    float a, b, c, d;
+                    upk2(o0, a, b);
+                    upk2(o1, c, d);
+                    yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+                }
+            }
+            __syncthreads();  // every warp has consumed this stage
+            if (threadIdx.x == 0 && i + kLnStages < my_tiles) issue(i + kLnStages);
+            continue;
+        }
         if (ok) {
             const float4* xp = reinterpret_cast<const float4*>(ln_smem + stage * kStageBytes + warp * D * 4);
             float4 v[NV];
@@ -276,44 +329,84 @@ ln_modulate_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, c
 // The same pass without the shared-memory ring (LFM_LN_ROWS=0): one row per warp straight from global memory into registers, 64
 // registers so that 32 warps are resident per SM (8 independent row chains per scheduler instead of 4), the grid sweeping M in
 // order (upwards, or downwards for order 2).  Same arithmetic in the same order as ln_modulate_kernel: identical results.
-template <int NV>
-__global__ void __launch_bounds__(256, 4)
+template <int NV, int THREADS = 256, int MINB = 4, bool X2 = false>
+__global__ void __launch_bounds__(THREADS, MINB)
 ln_modulate_direct_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ shift,
                           const float* __restrict__ scale, int mod_stride, int rows_per_sample, int M, int order_flags) {
+    // THREADS = 1024, MINB = 1 (LFM_LN_ROWS=32): the same 32 resident warps per SM as ONE persistent block per SM, which chains
+    // through programmatic dependent launch like the ring version does.
     constexpr int D = NV * 128;
+    constexpr int WARPS = THREADS / 32;
     pdl_wait();
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool down = (order_flags & 3) == 2;
-    for (int r = blockIdx.x * 8 + warp; r < M; r += gridDim.x * 8) {
+    for (int r = blockIdx.x * WARPS + warp; r < M; r += gridDim.x * WARPS) {
         const int row = down ? M - 1 - r : r;
         const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-        float4 v[NV];
-#pragma unroll
-        for (int m = 0; m < NV; ++m) v[m] = xp[m * 32 + lane];
-        float s = 0.f;
-#pragma unroll
-        for (int m = 0; m < NV; ++m) s += (v[m].x + v[m].y) + (v[m].z + v[m].w);
-        const float mean = warp_sum(s) / static_cast<float>(D);
-        float ss = 0.f;
-#pragma unroll
-        for (int m = 0; m < NV; ++m) {
-            const float a = v[m].x - mean, b = v[m].y - mean, c = v[m].z - mean, d = v[m].w - mean;
-            ss += (a * a + b * b) + (c * c + d * d);
-        }
-        const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + 1e-6f);
         const size_t boff = static_cast<size_t>(row / rows_per_sample) * mod_stride;
         const float4* shp = reinterpret_cast<const float4*>(shift + boff);
         const float4* scp = reinterpret_cast<const float4*>(scale + boff);
         uint2* yp = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+        if constexpr (X2) {
+            uint64_t pr[NV][2];
 #pragma unroll
-        for (int m = 0; m < NV; ++m) {
-            const float4 sh = __ldg(shp + m * 32 + lane), sc = __ldg(scp + m * 32 + lane);
-            const float a = fmaf((v[m].x - mean) * rstd, 1.f + sc.x, sh.x);
-            const float b = fmaf((v[m].y - mean) * rstd, 1.f + sc.y, sh.y);
-            const float c = fmaf((v[m].z - mean) * rstd, 1.f + sc.z, sh.z);
-            const float d = fmaf((v[m].w - mean) * rstd, 1.f + sc.w, sh.w);
-            yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+            for (int m = 0; m < NV; ++m) {
+                const float4 t4 = xp[m * 32 + lane];
+                pr[m][0] = pk2(t4.x, t4.y);
+                pr[m][1] = pk2(t4.z, t4.w);
+            }
+            uint64_t acc = pk2(0.f, 0.f);
+#pragma unroll
+            for (int m = 0; m < NV; ++m) acc = add2(acc, add2(pr[m][0], pr[m][1]));
+            float ax, ay;
+            upk2(acc, ax, ay);
+            const float mean = warp_sum(ax + ay) / static_cast<float>(D);
+            const uint64_t nmean = pk2(-mean, -mean);
+            uint64_t q0 = pk2(0.f, 0.f), q1 = pk2(0.f, 0.f);
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+                const uint64_t d0 = add2(pr[m][0], nmean), d1 = add2(pr[m][1], nmean);
+                q0 = fma2(d0, d0, q0);
+                q1 = fma2(d1, d1, q1);
+            }
+            float qx, qy;
+            upk2(add2(q0, q1), qx, qy);
+            const float rstd = rsqrtf(warp_sum(qx + qy) / static_cast<float>(D) + 1e-6f);
+            const uint64_t r2 = pk2(rstd, rstd), one2 = pk2(1.f, 1.f);
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+                const float4 sh = __ldg(shp + m * 32 + lane), sc = __ldg(scp + m * 32 + lane);
+                const uint64_t g0 = mul2(add2(pk2(sc.x, sc.y), one2), r2), g1 = mul2(add2(pk2(sc.z, sc.w), one2), r2);
+                float a, b, c, d;
+                upk2(fma2(add2(pr[m][0], nmean), g0, pk2(sh.x, sh.y)), a, b);
+                upk2(fma2(add2(pr[m][1], nmean), g1, pk2(sh.z, sh.w)), c, d);
+                yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+            }
+        } else {
+            float4 v[NV];
+#pragma unroll
+            for (int m = 0; m < NV; ++m) v[m] = xp[m * 32 + lane];
+            float s = 0.f;
+#pragma unroll
+            for (int m = 0; m < NV; ++m) s += (v[m].x + v[m].y) + (v[m].z + v[m].w);
+            const float mean = warp_sum(s) / static_cast<float>(D);
+            float ss = 0.f;
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+                const float a = v[m].x - mean, b = v[m].y - mean, c = v[m].z - mean, d = v[m].w - mean;
+                ss += (a * a + b * b) + (c * c + d * d);
+            }
+            const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + 1e-6f);
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+                const float4 sh = __ldg(shp + m * 32 + lane), sc = __ldg(scp + m * 32 + lane);
+                const float a = fmaf((v[m].x - mean) * rstd, 1.f + sc.x, sh.x);
+                const float b = fmaf((v[m].y - mean) * rstd, 1.f + sc.y, sh.y);
+                const float c = fmaf((v[m].z - mean) * rstd, 1.f + sc.z, sh.z);
+                const float d = fmaf((v[m].w - mean) * rstd, 1.f + sc.w, sh.w);
+                yp[m * 32 + lane] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+            }
         }
     }
 }

@@ -332,12 +332,12 @@ static cudaError_t launch_attention_inst(cudaStream_t s, const CUtensorMap& tq, 
     return cudaGetLastError();
 }
 
-template <int NV, int ROWS>
+template <int NV, int ROWS, bool X2 = false>
 static cudaError_t launch_ln_inst2(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
                                    int mod_stride, int rows_per_sample, int M, int order) {
     static DevOnce once;
     const int smem = ln_stages(NV, ROWS) * (ROWS + (ROWS == 16 ? 2 : 0)) * NV * 128 * 4;
-    auto kern = ln_modulate_kernel<NV, ROWS>;
+    auto kern = ln_modulate_kernel<NV, ROWS, X2>;
     if (cudaError_t e = smem_opt_in(once, kern, smem)) return e;
     const int tiles = (M + ROWS - 1) / ROWS;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
@@ -347,10 +347,18 @@ template <int NV>
 static cudaError_t launch_ln_inst(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
                                   int mod_stride, int rows_per_sample, int M, int order) {
     static const int rows = env_int("LFM_LN_ROWS", 16);  // same-box A/B (r2w): 116.99 / 116.72 img/s vs 116.33 / 116.34 with 8
+    static const int x2 = env_int("LFM_LN_X2", 0);  // packed f32x2 row arithmetic (A/B switch; see ln_modulate_kernel)
+    if (rows == 16 && x2) return launch_ln_inst2<NV, 16, true>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
     if (rows == 16) return launch_ln_inst2<NV, 16>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
     if (rows == 0) {
         const int blocks = std::min((M + 7) / 8, 4 * g_num_sms);
+        if (x2) return launch_k(ln_modulate_direct_kernel<NV, 256, 4, true>, dim3(blocks), 256, 0, s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
         return launch_k(ln_modulate_direct_kernel<NV>, dim3(blocks), 256, 0, s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
+    }
+    if (rows == 32) {  // one persistent 32-warp block per SM, rows straight from global memory
+        const int blocks = std::min((M + 31) / 32, g_num_sms);
+        if (x2) return launch_k(ln_modulate_direct_kernel<NV, 1024, 1, true>, dim3(blocks), 1024, 0, s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
+        return launch_k(ln_modulate_direct_kernel<NV, 1024, 1, false>, dim3(blocks), 1024, 0, s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
     }
     return launch_ln_inst2<NV, 8>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
 }
@@ -370,12 +378,16 @@ static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, con
                                      int variant = 2, int reverse = 0) {
     static DevOnce once2, once3;
     if (cudaError_t e = smem_opt_in(once2, attention2_t256_d64, kA2SmemBytes)) return e;
-    if (cudaError_t e = smem_opt_in(once3, attention3_t256_d64, kA2SmemBytes)) return e;
+    static DevOnce once3x;
+    static const int attn_x2 = env_int("LFM_ATTN_X2", 0);  // packed f32x2 softmax arithmetic (A/B switch)
+    if (cudaError_t e = smem_opt_in(once3, attention3_t256_d64<false>, kA2SmemBytes)) return e;
+    if (cudaError_t e = smem_opt_in(once3x, attention3_t256_d64<true>, kA2SmemBytes)) return e;
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
     if (variant == 3)
-        return launch_k(attention3_t256_d64, dim3(grid), kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
+        return launch_k(attn_x2 ? attention3_t256_d64<true> : attention3_t256_d64<false>, dim3(grid), kA2Threads, kA2SmemBytes, s, tkv,
+                        tout, D, H, items, scale_log2e, reverse);
     else
         attention2_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
     return cudaGetLastError();
