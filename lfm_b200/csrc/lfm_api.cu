@@ -380,14 +380,19 @@ static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, con
     if (cudaError_t e = smem_opt_in(once2, attention2_t256_d64, kA2SmemBytes)) return e;
     static DevOnce once3x;
     static const int attn_x2 = env_int("LFM_ATTN_X2", 0);  // packed f32x2 softmax arithmetic (A/B switch)
-    if (cudaError_t e = smem_opt_in(once3, attention3_t256_d64<false>, kA2SmemBytes)) return e;
-    if (cudaError_t e = smem_opt_in(once3x, attention3_t256_d64<true>, kA2SmemBytes)) return e;
+    static DevOnce once3s, once3xs;
+    static const int attn_split = env_int("LFM_ATTN_SPLIT", 0);  // S issued as two key halves, the first one early (A/B switch)
+    if (cudaError_t e = smem_opt_in(once3, attention3_t256_d64<false, false>, kA2SmemBytes)) return e;
+    if (cudaError_t e = smem_opt_in(once3x, attention3_t256_d64<true, false>, kA2SmemBytes)) return e;
+    if (cudaError_t e = smem_opt_in(once3s, attention3_t256_d64<false, true>, kA2SmemBytes)) return e;
+    if (cudaError_t e = smem_opt_in(once3xs, attention3_t256_d64<true, true>, kA2SmemBytes)) return e;
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
     if (variant == 3)
-        return launch_k(attn_x2 ? attention3_t256_d64<true> : attention3_t256_d64<false>, dim3(grid), kA2Threads, kA2SmemBytes, s, tkv,
-                        tout, D, H, items, scale_log2e, reverse);
+        return launch_k(attn_split ? (attn_x2 ? attention3_t256_d64<true, true> : attention3_t256_d64<false, true>)
+                                   : (attn_x2 ? attention3_t256_d64<true, false> : attention3_t256_d64<false, false>),
+                        dim3(grid), kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
     else
         attention2_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
     return cudaGetLastError();
