@@ -48,12 +48,7 @@ LFM_DEVICE float row_max128(const uint32_t (*v)[32]) {
 // X2 (LFM_ATTN_X2): the softmax / merge arithmetic in packed f32x2 instructions - per PAIR of scores one fma (scale, minus the row
 // maximum), two MUFU.EX2, one add into a packed partial sum and one bf16x2 conversion (5 issue slots instead of 7); same values, the
 // row sum is accumulated in a different (equally valid) order.
-// SPLIT (LFM_ATTN_SPLIT): S_g = Q_g K^T is issued as two N = 128 halves with their own barriers.  S_A of the NEXT head goes to the
-// tensor pipe right behind the P V MMAs of the current one (the pipe executes in issue order, so the P columns it overwrites have been
-// consumed) and runs while the softmax warps are still in the current head's epilogue; only S_B - whose columns hold O_A / O_B until the
-// epilogue has read them - waits for s_empty.  The softmax of the next head then starts without the S MMA + commit latency in front of
-// it, and S_B is computed under the exponentials of half A.
-template <bool X2, bool SPLIT = false>
+template <bool X2>
 __global__ void __launch_bounds__(kA2Threads, 1)
 attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D] bf16, box {64, 256}
                     const __grid_constant__ CUtensorMap tmap_out,  // out [M, D]  bf16, box {64, 128}
@@ -68,8 +63,7 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
     uint64_t* o_full = bars + 8;    // [2] MMA -> softmax WG g
     uint64_t* s_empty = bars + 10;  // [2] softmax WG g -> MMA   (128 arrivals): TMEM region g is free again
     uint64_t* pb_full = bars + 12;  // [2] softmax WG g -> MMA   (128 arrivals): P_B written
-    uint64_t* s_fullB = bars + 14;  // [2] (SPLIT) MMA -> softmax WG g: the second key half of S is in TMEM
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -86,7 +80,6 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
                 mbar_init(&o_full[i], 1);
                 mbar_init(&s_empty[i], 128);
                 mbar_init(&pb_full[i], 128);
-                mbar_init(&s_fullB[i], 1);
             }
             fence_barrier_init();
             fence_proxy_async();
@@ -130,35 +123,14 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
                 mbar_wait(&full[stage], (i >> 1) & 1);
                 tc_fence_after();
                 const uint64_t dk = make_smem_desc_sw128(smem_u32(st + kAttnKVBytes), 16, 1024);
-                if constexpr (SPLIT) {
-                    constexpr uint32_t idesc_h = make_idesc_bf16(128, 128, 0, 0);
-                    const uint64_t dkB = make_smem_desc_sw128(smem_u32(st + kAttnKVBytes + 128 * 128), 16, 1024);  // keys 128..255
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {  // S_A: columns [0,128) of region g held P of the previous head - consumed (issue order)
-                        const uint64_t dq = make_smem_desc_sw128(smem_u32(st + g * kAttnQBytes), 16, 1024);
+                for (int g = 0; g < 2; ++g) {
+                    mbar_wait(&s_empty[g], hp ^ 1);
+                    tc_fence_after();
+                    const uint64_t dq = make_smem_desc_sw128(smem_u32(st + g * kAttnQBytes), 16, 1024);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_ss(tmem + g * 256, dq + 2 * k, dk + 2 * k, idesc_h, k != 0);
-                        umma_commit(&s_full[g]);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {  // S_B: columns [128,256) hold O_A / O_B until the previous head's epilogue has read them
-                        mbar_wait(&s_empty[g], hp ^ 1);
-                        tc_fence_after();
-                        const uint64_t dq = make_smem_desc_sw128(smem_u32(st + g * kAttnQBytes), 16, 1024);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_ss(tmem + g * 256 + 128, dq + 2 * k, dkB + 2 * k, idesc_h, k != 0);
-                        umma_commit(&s_fullB[g]);
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        mbar_wait(&s_empty[g], hp ^ 1);
-                        tc_fence_after();
-                        const uint64_t dq = make_smem_desc_sw128(smem_u32(st + g * kAttnQBytes), 16, 1024);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_ss(tmem + g * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-                        umma_commit(&s_full[g]);
-                    }
+                    for (int k = 0; k < 4; ++k) umma_ss(tmem + g * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                    umma_commit(&s_full[g]);
                 }
                 // O_A = P_A V[0:128]  -> TMEM cols [128,192);  O_B = P_B V[128:256] -> cols [192,256)
 #pragma unroll
@@ -242,10 +214,6 @@ attention3_t256_d64(const __grid_constant__ CUtensorMap tmap_kv,   // qkv [M, 3D
             }
             {
                 uint32_t v[4][32];
-                if constexpr (SPLIT) {
-                    mbar_wait(&s_fullB[g], hp);
-                    tc_fence_after();
-                }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(taddr + 128 + c * 32, v[c]);
                 tmem_ld_wait();   // S_B in registers: columns [128,256) may now be overwritten by O_A / O_B

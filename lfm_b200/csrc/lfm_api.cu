@@ -347,7 +347,7 @@ template <int NV>
 static cudaError_t launch_ln_inst(cudaStream_t s, const float* x, __nv_bfloat16* y, const float* shift, const float* scale,
                                   int mod_stride, int rows_per_sample, int M, int order) {
     static const int rows = env_int("LFM_LN_ROWS", 16);  // same-box A/B (r2w): 116.99 / 116.72 img/s vs 116.33 / 116.34 with 8
-    static const int x2 = env_int("LFM_LN_X2", 0);  // packed f32x2 row arithmetic (A/B switch; see ln_modulate_kernel)
+    static const int x2 = env_int("LFM_LN_X2", 1);  // packed f32x2 row arithmetic: 18.9 -> 18.5 us per launch (profiles/r3c; see ln_modulate_kernel)
     if (rows == 16 && x2) return launch_ln_inst2<NV, 16, true>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
     if (rows == 16) return launch_ln_inst2<NV, 16>(s, x, y, shift, scale, mod_stride, rows_per_sample, M, order);
     if (rows == 0) {
@@ -379,20 +379,15 @@ static cudaError_t launch_attention2(cudaStream_t s, const CUtensorMap& tkv, con
     static DevOnce once2, once3;
     if (cudaError_t e = smem_opt_in(once2, attention2_t256_d64, kA2SmemBytes)) return e;
     static DevOnce once3x;
-    static const int attn_x2 = env_int("LFM_ATTN_X2", 0);  // packed f32x2 softmax arithmetic (A/B switch)
-    static DevOnce once3s, once3xs;
-    static const int attn_split = env_int("LFM_ATTN_SPLIT", 0);  // S issued as two key halves, the first one early (A/B switch)
-    if (cudaError_t e = smem_opt_in(once3, attention3_t256_d64<false, false>, kA2SmemBytes)) return e;
-    if (cudaError_t e = smem_opt_in(once3x, attention3_t256_d64<true, false>, kA2SmemBytes)) return e;
-    if (cudaError_t e = smem_opt_in(once3s, attention3_t256_d64<false, true>, kA2SmemBytes)) return e;
-    if (cudaError_t e = smem_opt_in(once3xs, attention3_t256_d64<true, true>, kA2SmemBytes)) return e;
+    static const int attn_x2 = env_int("LFM_ATTN_X2", 1);  // packed f32x2 softmax arithmetic: 40.4 -> 39.0 us per launch (profiles/r3c)
+    if (cudaError_t e = smem_opt_in(once3, attention3_t256_d64<false>, kA2SmemBytes)) return e;
+    if (cudaError_t e = smem_opt_in(once3x, attention3_t256_d64<true>, kA2SmemBytes)) return e;
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     const int items = B * H;
     const int grid = items < g_num_sms ? items : g_num_sms;
     if (variant == 3)
-        return launch_k(attn_split ? (attn_x2 ? attention3_t256_d64<true, true> : attention3_t256_d64<false, true>)
-                                   : (attn_x2 ? attention3_t256_d64<true, false> : attention3_t256_d64<false, false>),
-                        dim3(grid), kA2Threads, kA2SmemBytes, s, tkv, tout, D, H, items, scale_log2e, reverse);
+        return launch_k(attn_x2 ? attention3_t256_d64<true> : attention3_t256_d64<false>, dim3(grid), kA2Threads, kA2SmemBytes, s, tkv,
+                        tout, D, H, items, scale_log2e, reverse);
     else
         attention2_t256_d64<<<grid, kA2Threads, kA2SmemBytes, s>>>(tkv, tout, D, H, items, scale_log2e);
     return cudaGetLastError();
