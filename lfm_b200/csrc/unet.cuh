@@ -624,7 +624,8 @@ LFM_DEVICE void mma_bf16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_
 
 template <int T, int CH>
 __global__ void __launch_bounds__(128)
-attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int C, int heads, int n_items) {
+attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int C, int heads, int n_items,
+                     float scale_log2e /* <= 0: CH^-1/2 * log2(e); > 0: given (DiT-XL: CH = 80 is head_dim 72 padded) */) {
     pdl_wait();
     pdl_trigger();
     constexpr int ITEMS = T == 16 ? 4 : 1;  // (sample, head) pairs per block
@@ -686,7 +687,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    const float sl2 = rsqrtf(static_cast<float>(CH)) * 1.4426950408889634f;  // (ch^-1/4)^2 = 1/sqrt(ch), in log2 units
+    const float sl2 = scale_log2e > 0.f ? scale_log2e
+                                        : rsqrtf(static_cast<float>(CH)) * 1.4426950408889634f;  // (ch^-1/4)^2 = 1/sqrt(ch), in log2 units
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int j = 0; j < T / 8; ++j) {
