@@ -12,7 +12,7 @@
 // so the kernel is sized for correctness and decent speed, not for the tcgen05 roofline.
 #pragma once
 #include "common.cuh"
-#include "unet.cuh"
+// (ldmatrix / mma.sync / cp.async helpers: unet.cuh, included before this file by lfm_api.cu)
 
 namespace lfm {
 

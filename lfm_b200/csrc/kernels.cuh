@@ -892,23 +892,34 @@ final_layer_generic_kernel(const float* __restrict__ x, const float* __restrict_
 }
 
 // qkv rows of timm's Attention (out-feature = which * D + head * dh + d, models/DiT.py:120 / SURVEY D6) re-ordered ONCE at upload
-// into the head-major layout (head * 3 dh + which * dh + d) that the short-sequence kernel attention_mma_kernel reads
-// (used when the token grid is 4 x 4 or 8 x 8).
-LFM_DEVICE int dit_qkv_src_row(int r, int D, int dh) {
-    const int h = r / (3 * dh), which = (r % (3 * dh)) / dh, d = r % dh;
-    return which * D + h * dh + d;
-}
-__global__ void dit_qkv_weight_repack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int D, int dh) {
-    const size_t n = static_cast<size_t>(3) * D * D;
+// into the head-major layout (head * 3 dhp + which * dhp + d) that the mma.sync attention kernels read (token grids other than 16 x 16,
+// and head_dim 72).  dhp >= dh is the stored head width: DiT-XL's 72 channels are padded to 80 with zero rows, so q.k^T and P.V are
+// unchanged and the padded output channels are exactly zero; the proj weight gets matching zero columns.
+__global__ void dit_qkv_weight_repack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int D, int dh, int dhp) {
+    const int heads = D / dh;
+    const size_t n = static_cast<size_t>(3) * heads * dhp * D;
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int r = static_cast<int>(i / D), k = static_cast<int>(i % D);
-    out[i] = __float2bfloat16(w[static_cast<size_t>(dit_qkv_src_row(r, D, dh)) * D + k]);
+    const int h = r / (3 * dhp), which = (r % (3 * dhp)) / dhp, d = r % dhp;
+    out[i] = d < dh ? __float2bfloat16(w[static_cast<size_t>(which * D + h * dh + d) * D + k]) : __float2bfloat16(0.f);
 }
-__global__ void dit_qkv_bias_repack_kernel(const float* __restrict__ b, float* __restrict__ out, int D, int dh) {
+__global__ void dit_qkv_bias_repack_kernel(const float* __restrict__ b, float* __restrict__ out, int D, int dh, int dhp) {
+    const int heads = D / dh;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= 3 * D) return;
-    out[r] = b[dit_qkv_src_row(r, D, dh)];
+    if (r >= 3 * heads * dhp) return;
+    const int h = r / (3 * dhp), which = (r % (3 * dhp)) / dhp, d = r % dhp;
+    out[r] = d < dh ? b[which * D + h * dh + d] : 0.f;
+}
+// proj weight [D, D] -> [D, heads * dhp]: input feature head * dh + d moves to column head * dhp + d, zero columns for the padding
+__global__ void dit_proj_weight_pad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int D, int dh, int dhp) {
+    const int Dq = D / dh * dhp;
+    const size_t n = static_cast<size_t>(D) * Dq;
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = static_cast<int>(i / Dq), c = static_cast<int>(i % Dq);
+    const int h = c / dhp, d = c % dhp;
+    out[i] = d < dh ? __float2bfloat16(w[static_cast<size_t>(r) * D + h * dh + d]) : __float2bfloat16(0.f);
 }
 
 }  // namespace lfm

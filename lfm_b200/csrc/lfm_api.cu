@@ -23,6 +23,7 @@
 #include "gemm5.cuh"
 #include "kernels.cuh"
 #include "unet.cuh"
+#include "attention_flash.cuh"
 #include "vae.cuh"
 
 using namespace lfm;
@@ -406,7 +407,8 @@ struct ParamSlot {
     int kind = 0;  // 0 copy fp32, 1 cast bf16, 2 conv [Co,Ci,kh,kw] -> bf16 [Co,kh,kw,Ci], 3 out-conv -> fp32 [4][9][C],
                    // 4 fp32 transpose [R, rest] -> [rest, R], 5 / 6 EDM qkv weight / bias row re-order (aux0 = head dim,
                    // aux1 = target layout), 7 constant resample_filter (validated, not stored), 8 / 9 DiT qkv weight / bias rows
-                   // re-ordered head-major for the short-sequence attention kernel (aux0 = head dim)
+                   // re-ordered head-major for the mma.sync attention kernels (aux0 = head dim, aux1 = its stored, zero-padded width),
+                   // 10 DiT proj weight with zero columns for the padded head channels
     int aux0 = 0, aux1 = 0;
     bool set = false;
 };
@@ -427,6 +429,8 @@ struct lfm_ctx {
     int device = 0;
     int num_sms = 0;
     int D = 0, L = 0, H = 0, T = 0, G = 0, C = 0, Hd = 0, Nmod = 0, HW = 0, chw = 0;
+    int dh = 64, dhp = 64, Dq = 0;  // head_dim, its stored (zero-padded) width and the width H * dhp of the attention tensors
+    bool qkv_head_major = false;    // qkv rows re-ordered for the mma.sync attention kernels (everything but T = 256 with head_dim 64)
     int max_rows = 0;
     bool finalized = false;
     std::string err;
@@ -525,22 +529,22 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     if (desc == nullptr || out == nullptr) return fail(nullptr, "lfm_create: null argument");
     if (desc->arch != LFM_ARCH_DIT) return fail(nullptr, "lfm_create: unsupported arch %d", desc->arch);
     // Geometries (models/DiT.py:355-415; img_resolution = image_size // f): patch 2 / 4 / 8 on latents whose token grid is
-    // 4 x 4, 8 x 8 or 16 x 16 - e.g. /2 on 32 x 32 (every released preset), /4 on 64 x 64 or 32 x 32, /8 on 32 x 32.
+    // 4 x 4, 8 x 8, 16 x 16 or 32 x 32 - e.g. /2 on 32 x 32 (every released preset) or 64 x 64, /4 on 64 x 64 or 32 x 32, /8 on 32 x 32.
     if (desc->patch_size != 2 && desc->patch_size != 4 && desc->patch_size != 8)
         return fail(nullptr, "lfm_create: patch_size must be 2, 4 or 8 (got %d)", desc->patch_size);
     {
         const int g = desc->img_resolution / desc->patch_size;
-        if (desc->img_resolution <= 0 || desc->img_resolution % desc->patch_size != 0 || !(g == 4 || g == 8 || g == 16))
-            return fail(nullptr, "lfm_create: the token grid (img_resolution / patch_size) must be 4, 8 or 16 per side, i.e. 16, 64 or "
-                        "256 tokens (got img_resolution %d, patch_size %d)", desc->img_resolution, desc->patch_size);
+        if (desc->img_resolution <= 0 || desc->img_resolution % desc->patch_size != 0 || !(g == 4 || g == 8 || g == 16 || g == 32))
+            return fail(nullptr, "lfm_create: the token grid (img_resolution / patch_size) must be 4, 8, 16 or 32 per side, i.e. 16, 64, "
+                        "256 or 1024 tokens (got img_resolution %d, patch_size %d)", desc->img_resolution, desc->patch_size);
     }
     {
         const int nv = desc->hidden_size / 128;
         if (desc->hidden_size % 128 != 0 || !(nv == 2 || nv == 3 || nv == 6 || nv == 8 || nv == 9))
             return fail(nullptr, "lfm_create: hidden_size must be one of 256, 384, 768, 1024, 1152 (got %d)", desc->hidden_size);
     }
-    if (desc->num_heads * 64 != desc->hidden_size)
-        return fail(nullptr, "lfm_create: head_dim must be 64 (hidden %d, heads %d)", desc->hidden_size, desc->num_heads);
+    if (desc->num_heads <= 0 || (desc->num_heads * 64 != desc->hidden_size && desc->num_heads * 72 != desc->hidden_size))
+        return fail(nullptr, "lfm_create: head_dim must be 64 or 72 (hidden %d, heads %d)", desc->hidden_size, desc->num_heads);
     if (desc->mlp_hidden % 64 != 0) return fail(nullptr, "lfm_create: mlp_hidden must be a multiple of 64");
     if (desc->in_channels != 4) return fail(nullptr, "lfm_create: in_channels must be 4");
     int ndev = 0;
@@ -572,8 +576,14 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
     const int ps = desc->patch_size;
     const int P = ctx->C * ps * ps;  // elements of one patch = out-features of the final linear
-    // 4 x 4 / 8 x 8 token grids run attention on the short-sequence mma.sync kernel, which reads head-major qkv rows
-    const bool qkv_head_major = T != 256;
+    // Only 256 tokens with head_dim 64 run on the tcgen05 attention kernel (native timm qkv order).  Everything else - 16 / 64 / 1024
+    // tokens, head_dim 72 (DiT-XL, stored padded to 80) - runs on the mma.sync kernels, which read head-major qkv rows.
+    ctx->dh = desc->hidden_size / desc->num_heads;
+    ctx->dhp = ctx->dh == 72 ? 80 : 64;
+    ctx->Dq = desc->num_heads * ctx->dhp;
+    ctx->qkv_head_major = (T != 256 || ctx->dh != 64);
+    const bool qkv_head_major = ctx->qkv_head_major;
+    const int Dq = ctx->Dq;
 
     if (dev_alloc(ctx, &ctx->pos, (size_t)T * D)) return 1;
     if (dev_alloc(ctx, &ctx->pe_w, (size_t)D * P)) return 1;
@@ -602,23 +612,26 @@ extern "C" int lfm_create(const lfm_model_desc* desc, int device, lfm_ctx** out)
     ctx->blk.resize(L);
     for (int i = 0; i < L; ++i) {
         BlockW& b = ctx->blk[i];
-        if (dev_alloc(ctx, &b.w_qkv, (size_t)3 * D * D)) return 1;
-        if (dev_alloc(ctx, &b.w_proj, (size_t)D * D)) return 1;
+        if (dev_alloc(ctx, &b.w_qkv, (size_t)3 * Dq * D)) return 1;
+        if (dev_alloc(ctx, &b.w_proj, (size_t)D * Dq)) return 1;
         if (dev_alloc(ctx, &b.w_fc1, (size_t)Hd * D)) return 1;
         if (dev_alloc(ctx, &b.w_fc2, (size_t)D * Hd)) return 1;
-        if (dev_alloc(ctx, &b.b_qkv, 3 * D)) return 1;
+        if (dev_alloc(ctx, &b.b_qkv, 3 * Dq)) return 1;
         if (dev_alloc(ctx, &b.b_proj, D)) return 1;
         if (dev_alloc(ctx, &b.b_fc1, Hd)) return 1;
         if (dev_alloc(ctx, &b.b_fc2, D)) return 1;
         const std::string p = "blocks." + std::to_string(i) + ".";
         if (qkv_head_major) {
-            add_param_aux(ctx, p + "attn.qkv.weight", b.w_qkv, {3 * D, D}, 8, 64, 0);
-            add_param_aux(ctx, p + "attn.qkv.bias", b.b_qkv, {3 * D}, 9, 64, 0);
+            add_param_aux(ctx, p + "attn.qkv.weight", b.w_qkv, {3 * D, D}, 8, ctx->dh, ctx->dhp);
+            add_param_aux(ctx, p + "attn.qkv.bias", b.b_qkv, {3 * D}, 9, ctx->dh, ctx->dhp);
         } else {
             add_param(ctx, p + "attn.qkv.weight", b.w_qkv, {3 * D, D}, true);
             add_param(ctx, p + "attn.qkv.bias", b.b_qkv, {3 * D}, false);
         }
-        add_param(ctx, p + "attn.proj.weight", b.w_proj, {D, D}, true);
+        if (ctx->dhp != ctx->dh)
+            add_param_aux(ctx, p + "attn.proj.weight", b.w_proj, {D, D}, 10, ctx->dh, ctx->dhp);  // zero columns for the padded channels
+        else
+            add_param(ctx, p + "attn.proj.weight", b.w_proj, {D, D}, true);
         add_param(ctx, p + "attn.proj.bias", b.b_proj, {D}, false);
         add_param(ctx, p + "mlp.fc1.weight", b.w_fc1, {Hd, D}, true);
         add_param(ctx, p + "mlp.fc1.bias", b.b_fc1, {Hd}, false);
@@ -673,12 +686,18 @@ extern "C" int lfm_set_param(lfm_ctx* ctx, const char* key, const void* ptr, int
         } else if (s.kind == 6) {
             edm_qkv_bias_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<float*>(s.dst),
                                                                     static_cast<int>(s.shape[0] / 3), s.aux0, s.aux1);
-        } else if (s.kind == 8) {
-            dit_qkv_weight_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst),
-                                                                      static_cast<int>(s.shape[1]), s.aux0);
+        } else if (s.kind == 8) {  // aux0 = head_dim, aux1 = stored head width: the destination has 3 * heads * aux1 rows
+            const int Dm = static_cast<int>(s.shape[1]);
+            const size_t out_n = static_cast<size_t>(3) * (Dm / s.aux0) * s.aux1 * Dm;
+            dit_qkv_weight_repack_kernel<<<blocks_for(out_n), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst), Dm, s.aux0, s.aux1);
         } else if (s.kind == 9) {
-            dit_qkv_bias_repack_kernel<<<blocks_for(s.numel), 256>>>(ctx->staging, static_cast<float*>(s.dst),
-                                                                    static_cast<int>(s.shape[0] / 3), s.aux0);
+            const int Dm = static_cast<int>(s.shape[0] / 3);
+            dit_qkv_bias_repack_kernel<<<blocks_for(static_cast<size_t>(3) * (Dm / s.aux0) * s.aux1), 256>>>(
+                ctx->staging, static_cast<float*>(s.dst), Dm, s.aux0, s.aux1);
+        } else if (s.kind == 10) {
+            const int Dm = static_cast<int>(s.shape[0]);
+            const size_t out_n = static_cast<size_t>(Dm) * (Dm / s.aux0) * s.aux1;
+            dit_proj_weight_pad_kernel<<<blocks_for(out_n), 256>>>(ctx->staging, static_cast<__nv_bfloat16*>(s.dst), Dm, s.aux0, s.aux1);
         } else if (s.kind == 7) {
             float h[4] = {0.f, 0.f, 0.f, 0.f};
             CUDA_OK(cudaMemcpy(h, ctx->staging, sizeof(h), cudaMemcpyDeviceToHost));
@@ -741,13 +760,13 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
         ctx->finalized = true;
         return 0;
     }
-    const int D = ctx->D, Hd = ctx->Hd, T = ctx->T, R = max_batch;
+    const int D = ctx->D, Hd = ctx->Hd, T = ctx->T, R = max_batch, Dq = ctx->Dq;
     const size_t M = (size_t)R * T;
     const int Rpad = R < 128 ? 128 : R;
     if (dev_alloc(ctx, &ctx->x_tok, M * D)) return 1;
     if (dev_alloc(ctx, &ctx->xn, M * D)) return 1;
-    if (dev_alloc(ctx, &ctx->qkv, M * 3 * D)) return 1;
-    if (dev_alloc(ctx, &ctx->attn, M * D)) return 1;
+    if (dev_alloc(ctx, &ctx->qkv, M * 3 * Dq)) return 1;
+    if (dev_alloc(ctx, &ctx->attn, M * Dq)) return 1;
     if (dev_alloc(ctx, &ctx->hmid, M * Hd)) return 1;
     if (dev_alloc(ctx, &ctx->mod, (size_t)R * ctx->Nmod)) return 1;
     if (dev_alloc(ctx, &ctx->c_silu, (size_t)Rpad * D)) return 1;
@@ -773,25 +792,25 @@ extern "C" int lfm_finalize(lfm_ctx* ctx, int max_batch) {
     ctx->bn_mod = 256;
     bool ok = true;
     ok &= make_tmap_bf16(&ctx->tm_xn, ctx->xn, M, D, 128);
-    ok &= make_tmap_bf16(&ctx->tm_attn, ctx->attn, M, D, 128);
+    ok &= make_tmap_bf16(&ctx->tm_attn, ctx->attn, M, Dq, 128);
     ok &= make_tmap_bf16(&ctx->tm_hmid, ctx->hmid, M, Hd, 128);
     ok &= make_tmap_bf16(&ctx->tm_csilu, ctx->c_silu, Rpad, D, 128);
-    ok &= make_tmap_bf16(&ctx->tm_qkv_q, ctx->qkv, M, 3 * D, 128);
-    ok &= make_tmap_bf16(&ctx->tm_qkv_kv, ctx->qkv, M, 3 * D, 256);
+    ok &= make_tmap_bf16(&ctx->tm_qkv_q, ctx->qkv, M, 3 * Dq, 128);
+    ok &= make_tmap_bf16(&ctx->tm_qkv_kv, ctx->qkv, M, 3 * Dq, 256);
     ok &= make_tmap_bf16(&ctx->tm_wmod, ctx->w_mod, ctx->Nmod, D, ctx->bn_mod);
     ok &= make_tmap_bf16(&ctx->tm64_xn, ctx->xn, M, D, 64);
-    ok &= make_tmap_bf16(&ctx->tm64_attn, ctx->attn, M, D, 64);
+    ok &= make_tmap_bf16(&ctx->tm64_attn, ctx->attn, M, Dq, 64);
     ok &= make_tmap_bf16(&ctx->tm64_hmid, ctx->hmid, M, Hd, 64);
-    ok &= make_tmap_out(&ctx->tmo_qkv, ctx->qkv, M, 3 * D, false);
+    ok &= make_tmap_out(&ctx->tmo_qkv, ctx->qkv, M, 3 * Dq, false);
     ok &= make_tmap_out(&ctx->tmo_hmid, ctx->hmid, M, Hd, false);
     ok &= make_tmap_out(&ctx->tmo_xtok, ctx->x_tok, M, D, true);
     for (auto& b : ctx->blk) {
-        ok &= make_tmap_bf16(&b.tm_qkv, b.w_qkv, 3 * D, D, weight_box_rows(ctx->bn_qkv));
-        ok &= make_tmap_bf16(&b.tm_proj, b.w_proj, D, D, weight_box_rows(ctx->bn_proj));
+        ok &= make_tmap_bf16(&b.tm_qkv, b.w_qkv, 3 * Dq, D, weight_box_rows(ctx->bn_qkv));
+        ok &= make_tmap_bf16(&b.tm_proj, b.w_proj, D, Dq, weight_box_rows(ctx->bn_proj));
         ok &= make_tmap_bf16(&b.tm_fc1, b.w_fc1, Hd, D, weight_box_rows(ctx->bn_fc1));
         ok &= make_tmap_bf16(&b.tm_fc2, b.w_fc2, D, Hd, weight_box_rows(ctx->bn_fc2));
-        ok &= make_tmap_bf16(&b.tmh_qkv, b.w_qkv, 3 * D, D, 64);
-        ok &= make_tmap_bf16(&b.tmh_proj, b.w_proj, D, D, 64);
+        ok &= make_tmap_bf16(&b.tmh_qkv, b.w_qkv, 3 * Dq, D, 64);
+        ok &= make_tmap_bf16(&b.tmh_proj, b.w_proj, D, Dq, 64);
         ok &= make_tmap_bf16(&b.tmh_fc1, b.w_fc1, Hd, D, 64);
         ok &= make_tmap_bf16(&b.tmh_fc2, b.w_fc2, D, Hd, 64);
     }
@@ -825,7 +844,7 @@ static int ctx_unet_variant(const lfm_ctx* ctx) { return ctx->un != nullptr ? ct
 static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_numel, const float* x, int x_rows,
                           const long long* y, int rows) {
     if (ctx->arch == LFM_ARCH_UNET) return launch_unet(ctx, s, t, t_numel, x, x_rows, y, rows);
-    const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T;
+    const int D = ctx->D, L = ctx->L, Hd = ctx->Hd, T = ctx->T, Dq = ctx->Dq;
     const int M = rows * T;
     // Conditioning c = t_emb(t) + y_emb(y) and the adaLN tables.  A 0-d t with y = None (every unconditional
     // preset) gives the same c for every row: compute ONE row and let all samples read it (table stride 0).
@@ -878,17 +897,22 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
             ctx->launches++;
         }
         {
-            GemmEpi ep{b.b_qkv, ctx->qkv, 3 * D, nullptr, 0, T};
+            GemmEpi ep{b.b_qkv, ctx->qkv, 3 * Dq, nullptr, 0, T};
             ep.dbg_flags = g2_flags;
             ep.reverse_m = next_dir();
-            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * D, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv, &b.tmh_qkv, &ctx->tm64_xn));
+            CUDA_OK(launch_gemm(s, ctx->tm_xn, b.tm_qkv, M, 3 * Dq, D, EPI_BIAS_BF16, ctx->bn_qkv, ep, &ctx->tmo_qkv, &b.tmh_qkv, &ctx->tm64_xn));
             ctx->launches++;
         }
         {
             const int d = next_dir();
-            if (T != 256)  // 4 x 4 / 8 x 8 token grids: warp-level mma.sync kernel on head-major qkv rows (see lfm_create)
-                CUDA_OK(launch_attention_mma(s, ctx->qkv, ctx->attn, T, 64, D, ctx->H, rows * ctx->H));
-            else if (ctx->attn_variant >= 2)
+            if (ctx->qkv_head_major) {  // mma.sync kernels on head-major qkv rows (see lfm_create)
+                // head_dim 64 keeps the kernel's own ch^-1/2; the padded DiT-XL heads pass the true head_dim^-1/2
+                const float sc = 1.4426950408889634f / sqrtf(static_cast<float>(ctx->dh));
+                if (T == 16 || T == 64)   // 4 x 4 / 8 x 8 token grids: the whole sequence in registers
+                    CUDA_OK(launch_attention_mma(s, ctx->qkv, ctx->attn, T, ctx->dhp, Dq, ctx->H, rows * ctx->H, ctx->dh == 64 ? 0.f : sc));
+                else                      // 256 tokens with head_dim 72, 1024 tokens: keys streamed in chunks of 64
+                    CUDA_OK(launch_attention_flash(s, ctx->qkv, ctx->attn, T, ctx->dhp, Dq, ctx->H, rows * ctx->H, sc));
+            } else if (ctx->attn_variant >= 2)
                 CUDA_OK(launch_attention2(s, ctx->tm_qkv_kv, ctx->tm_attn, rows, ctx->H, D, ctx->attn_variant, d));
             else if (ctx->attn_variant == 0)
                 CUDA_OK(launch_attention_inst<true>(s, ctx->tm_qkv_q, ctx->tm_qkv_kv, ctx->attn, rows, ctx->H, D, nullptr));
@@ -911,7 +935,7 @@ static int launch_network(lfm_ctx* ctx, cudaStream_t s, const float* t, int t_nu
                 ep.ln_scale = mb + 4 * D;
                 ep.ln_stride = Nmod;
             }
-            CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, D, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok, &b.tmh_proj, &ctx->tm64_attn));
+            CUDA_OK(launch_gemm(s, ctx->tm_attn, b.tm_proj, M, D, Dq, EPI_GATE_RESID_F32, ctx->bn_proj, ep, &ctx->tmo_xtok, &b.tmh_proj, &ctx->tm64_attn));
             ctx->launches++;
         }
         if (!fuse) {
@@ -1624,6 +1648,24 @@ extern "C" int lfm_dbg_attention(const void* qkv_bf16, void* out_bf16, int B, in
         CUDA_OK(launch_attention_inst<true>(s, tq, tkv, static_cast<__nv_bfloat16*>(out_bf16), B, H, D, dbg_s));
     else
         CUDA_OK(launch_attention_inst<false>(s, tq, tkv, static_cast<__nv_bfloat16*>(out_bf16), B, H, D, dbg_s));
+    return 0;
+}
+
+extern "C" int lfm_dbg_attention_mma(const void* qkv_bf16, void* out_bf16, int B, int H, int T, int ch, int head_dim, void* stream) {
+    lfm_ctx* ctx = nullptr;
+    g_num_sms = query_num_sms();
+    if (g_num_sms <= 0) return fail(ctx, "no CUDA device");
+    if (!(ch == 64 || ch == 80) || head_dim <= 0 || head_dim > ch) return fail(ctx, "lfm_dbg_attention_mma: ch must be 64 or 80, head_dim <= ch");
+    const float sc = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv_bf16);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
+    if (T == 16 || T == 64)
+        CUDA_OK(launch_attention_mma(s, q, o, T, ch, H * ch, H, B * H, sc));
+    else if (T > 0 && T % 64 == 0)
+        CUDA_OK(launch_attention_flash(s, q, o, T, ch, H * ch, H, B * H, sc));
+    else
+        return fail(ctx, "lfm_dbg_attention_mma: T must be 16 or a multiple of 64 (got %d)", T);
     return 0;
 }
 

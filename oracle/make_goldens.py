@@ -59,6 +59,13 @@ GEOMETRY_CASES = {
                         label_dropout=0.0, num_classes=1), 23),
     "mini_r16p2": (dict(depth=2, hidden_size=256, patch_size=2, num_heads=4, img_resolution=16, in_channels=4,
                         label_dropout=0.1, num_classes=5), 24),
+    # head_dim 72 (the DiT-XL width, two blocks) at 256 and 64 tokens, and a 1024-token grid (64 x 64 latents, patch 2)
+    "mini_xl2": (dict(depth=2, hidden_size=1152, patch_size=2, num_heads=16, img_resolution=32, in_channels=4,
+                      label_dropout=0.0, num_classes=1), 25),
+    "mini_xl4": (dict(depth=2, hidden_size=1152, patch_size=4, num_heads=16, img_resolution=32, in_channels=4,
+                      label_dropout=0.1, num_classes=7), 26),
+    "mini_r64p2": (dict(depth=2, hidden_size=256, patch_size=2, num_heads=4, img_resolution=64, in_channels=4,
+                        label_dropout=0.0, num_classes=1), 27),
 }
 FULL = {
     "dit_l2": ("DiT-L/2", dict(img_resolution=32, in_channels=4, label_dropout=0.0, num_classes=1), 1),

@@ -115,12 +115,34 @@ def test_attention(dev, variant, B, H):
     assert rel_l2(out.float().cpu(), ref.cpu()) < 5e-3   # P and O are rounded to bf16
 
 
+@pytest.mark.parametrize("B,H,T,ch,dh", [(2, 4, 1024, 64, 64), (3, 16, 256, 80, 72), (2, 3, 256, 64, 64), (5, 16, 64, 80, 72),
+                                         (7, 16, 16, 80, 72), (1, 2, 128, 80, 72)])
+def test_attention_mma_kernels(dev, B, H, T, ch, dh):
+    """The mma.sync attention kernels of the DiT geometries outside T = 256 / head_dim 64 (head-major qkv rows, heads zero-padded from dh
+    to ch channels) against softmax(q k^T / sqrt(dh)) v in fp32 on the same bf16 operands."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B * 1000 + T + ch)
+    qkv = torch.randn(B, T, H, 3, ch, generator=g)
+    qkv[..., dh:] = 0                                            # the padding channels are zero (zero weight rows)
+    qkv = qkv.reshape(B * T, H * 3 * ch).to(dev).bfloat16()
+    q, k, v = qkv.float().reshape(B, T, H, 3, ch).permute(3, 0, 2, 1, 4)    # [B, H, T, ch] each
+    ref = (torch.softmax((q @ k.transpose(-1, -2)) * dh ** -0.5, dim=-1) @ v).transpose(1, 2).reshape(B * T, H * ch)
+    out = torch.full((B * T, H * ch), 7.0, device=dev, dtype=torch.bfloat16)
+    rc = lib.lfm_dbg_attention_mma(P(qkv), P(out), B, H, T, ch, dh, None)
+    torch.cuda.synchronize()
+    assert rc == 0, _lib.last_error()
+    assert rel_l2(out.float().cpu(), ref.cpu()) < 5e-3           # P and O are rounded to bf16
+    assert float(out.float().reshape(B * T, H, ch)[..., dh:].abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------------------------------------ reference fixtures
 
 
 # patch 4 / 8 and other latent sides: token grids 8 x 8 / 4 x 4 (short-sequence attention kernel on head-major qkv rows, generic
 # patch-embed / final-layer kernels) and 16 x 16 with patch 4 on 64 x 64 latents (oracle/make_goldens.py patch)
-GEOMETRY = ["mini_p4", "mini_p8", "mini_r64p4", "mini_r16p2"]
+GEOMETRY = ["mini_p4", "mini_p8", "mini_r64p4", "mini_r16p2",
+            # head_dim 72 (the DiT-XL width: heads stored padded to 80 channels) at 256 / 64 tokens; 1024 tokens (64 x 64 latents, /2)
+            "mini_xl2", "mini_xl4", "mini_r64p2"]
 
 
 @pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"] + GEOMETRY)

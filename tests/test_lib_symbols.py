@@ -55,12 +55,12 @@ def test_create_fails_loudly_without_gpu(lib):
 def test_unsupported_shapes_are_rejected(lib):
     from lfm_b200 import _lib
     ctx = ctypes.c_void_p()
-    bad = _lib.ModelDesc(0, 32, 2, 4, 1152, 28, 16, 4608, 1)  # head_dim 72 (DiT-XL): not implemented
+    bad = _lib.ModelDesc(0, 32, 2, 4, 1024, 24, 8, 4096, 1)  # head_dim 128: only 64 and 72 (the reference's size table) are implemented
     assert lib.lfm_create(ctypes.byref(bad), 0, ctypes.byref(ctx)) != 0
     assert "head_dim" in _lib.last_error()
     bad = _lib.ModelDesc(0, 32, 3, 4, 1024, 24, 16, 4096, 1)  # patch 3 (the reference's table has 2, 4, 8)
     assert lib.lfm_create(ctypes.byref(bad), 0, ctypes.byref(ctx)) != 0
     assert "patch_size" in _lib.last_error()
-    bad = _lib.ModelDesc(0, 64, 2, 4, 1024, 24, 16, 4096, 1)  # 64 x 64 latents with patch 2: 1024 tokens, not implemented
+    bad = _lib.ModelDesc(0, 128, 2, 4, 1024, 24, 16, 4096, 1)  # 128 x 128 latents with patch 2: 4096 tokens, not implemented
     assert lib.lfm_create(ctypes.byref(bad), 0, ctypes.byref(ctx)) != 0
     assert "token grid" in _lib.last_error()

@@ -15,7 +15,8 @@ from tests._util import T, cfg_from_golden, load_golden, oracle_model, rel_l2
 TOL = 2e-5
 
 
-GEOMETRY = ["mini_p4", "mini_p8", "mini_r64p4", "mini_r16p2"]   # patch 4 / 8 and other latent sides (make_goldens.py patch)
+# patch 4 / 8, other latent sides, head_dim 72 and a 1024-token grid (make_goldens.py patch)
+GEOMETRY = ["mini_p4", "mini_p8", "mini_r64p4", "mini_r16p2", "mini_xl2", "mini_xl4", "mini_r64p2"]
 
 
 @pytest.mark.parametrize("name", ["mini_uncond", "mini_cond", "mini_d384"] + GEOMETRY)
@@ -31,7 +32,7 @@ def test_forward_matches_reference(name):
     assert float(np.abs(g["v_vec_y"]).mean()) > 1e-3  # synthetic init is non-degenerate
 
 
-@pytest.mark.parametrize("name", ["mini_cond", "mini_d384", "mini_p4", "mini_r16p2"])
+@pytest.mark.parametrize("name", ["mini_cond", "mini_d384", "mini_p4", "mini_r16p2", "mini_xl4"])
 def test_cfg_matches_reference(name):
     g = load_golden(name)
     cfg = cfg_from_golden(g)
