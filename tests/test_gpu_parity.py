@@ -132,7 +132,8 @@ def test_attention_mma_kernels(dev, B, H, T, ch, dh):
     torch.cuda.synchronize()
     assert rc == 0, _lib.last_error()
     assert rel_l2(out.float().cpu(), ref.cpu()) < 5e-3           # P and O are rounded to bf16
-    assert float(out.float().reshape(B * T, H, ch)[..., dh:].abs().max()) == 0.0
+    if ch > dh:
+        assert float(out.float().reshape(B * T, H, ch)[..., dh:].abs().max()) == 0.0   # padded output channels are exactly zero
 
 
 # ------------------------------------------------------------------------------------------------ reference fixtures
