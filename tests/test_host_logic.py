@@ -34,6 +34,19 @@ def test_state_dict_surface_matches_reference_keys():
     assert len(big.state_dict()) == 252
 
 
+def test_every_dit_models_entry_has_the_reference_key_table():
+    """All twelve entries of models/DiT.py:355-415 (patch 2 / 4 / 8, head_dim 64 and 72) at latent sides 32 and 64: same keys, shapes and order
+    as the oracle's table, which the reference modules pin for these geometries too (tests/golden/mini_p4 ... mini_r64p2)."""
+    for name, kw in odit.DIT_PRESETS.items():
+        for side in (32, 64):
+            with torch.device("meta"):
+                net = lfm_b200.DiT_models[name](img_resolution=side, in_channels=4, label_dropout=0.1, num_classes=1000)
+            cfg = odit.make_config(name, img_resolution=side, label_dropout=0.1, num_classes=1000)
+            want = odit.param_shapes(cfg)
+            got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+            assert got == want and list(got) == list(want), (name, side)
+
+
 def test_reference_init_is_degenerate_and_synthetic_is_not():
     net = _mini()
     assert float(net.final_layer.linear.weight.abs().max()) == 0.0          # models/DiT.py:225-228
