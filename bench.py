@@ -100,11 +100,11 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm)}
 
 
-def build_model(device, model=MODEL, num_classes=1, label_dropout=0.0, max_batch=BATCH):
+def build_model(device, model=MODEL, num_classes=1, label_dropout=0.0, max_batch=BATCH, latent_side=32):
     import lfm_b200
     from lfm_b200.synthetic import synthetic_state_dict
     with torch.device("meta"):
-        net = lfm_b200.DiT_models[model](img_resolution=32, in_channels=4, label_dropout=label_dropout, num_classes=num_classes)
+        net = lfm_b200.DiT_models[model](img_resolution=latent_side, in_channels=4, label_dropout=label_dropout, num_classes=num_classes)
     sd = synthetic_state_dict(net, WEIGHT_SEED)
     net = net.to_empty(device="cpu")
     net.load_state_dict(sd, strict=True)
@@ -550,6 +550,23 @@ def main():
                              "tflops_per_gpu": round(st["nfe"] * 32 * FLOPS_UNET_CELEB512 / ms / 1e9, 1)}
             del nu
             torch.cuda.empty_cache()
+            # Not BASELINE configurations: the two DiT geometries outside (256 tokens, head_dim 64) - DiT-XL/2 (head_dim 72) and DiT-L/2 on
+            # 64 x 64 latents (1024 tokens, 512-pixel images) - whose attention runs on the mma.sync flash kernel.  Euler-10, one GPU.
+            for key, model, side, per_gpu in (("dit_xl2", "DiT-XL/2", 32, 64), ("dit_l2_64x64_latents", "DiT-L/2", 64, 16)):
+                ng = build_model(device, model, 1, 0.0, per_gpu, latent_side=side)
+                xg = torch.randn(per_gpu, 4, side, side, generator=torch.Generator().manual_seed(17)).to(device)
+                ag = types.SimpleNamespace(method="euler", step_size=0.1, perturb=False, cfg_scale=1.0, compute_nfe=False)
+                fng = lambda: lfm_b200.sample_from_model(ng, xg, {}, ag)[-1]  # noqa: E731
+                fng()
+                ms, _ = timed(fng, 2, ng)
+                ms /= 2
+                T_, D_, L_ = (side // 2) ** 2, ng.hidden_size, ng.depth
+                fl = L_ * (24 * T_ * D_ * D_ + 4 * T_ * T_ * D_ + 12 * D_ * D_) + 4 * T_ * 16 * D_ + 2 * (256 * D_ + D_ * D_) + 4 * D_ * D_
+                other[key] = {"what": f"{model} on {side}x{side} latents ({T_} tokens, head_dim {D_ // ng.num_heads}), Euler-10, batch {per_gpu}, 1 GPU",
+                              "images_per_s": round(per_gpu / ms * 1e3, 2), "ms_per_pass": round(ms, 2),
+                              "tflops_per_gpu": round(10 * per_gpu * fl / ms / 1e9, 1), "flops_per_sample_per_nfe": fl}
+                del ng
+                torch.cuda.empty_cache()
 
     if rank == 0:
         imgs = BATCH * world * args.steps

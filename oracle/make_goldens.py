@@ -162,6 +162,9 @@ EDM_CASES = {
     # the ffhq_adm / bed_adm preset at full width (test_args/ffhq_adm.txt: nf 256, ch_mult 1 2 3 4, attn 16 8 4)
     "edm_ffhq": (dict(img_resolution=32, label_dim=0, model_channels=256, channel_mult=(1, 2, 3, 4), num_blocks=2,
                       attn_resolutions=(16, 8, 4)), 1, 1),
+    # self-attention on the 32 x 32 grid (1024 tokens; the constructor's default attn_resolutions start at 32, EDM.py:723)
+    "edm_attn32": (dict(img_resolution=32, label_dim=0, model_channels=128, channel_mult=(1, 2), num_blocks=1,
+                        attn_resolutions=(32, 16)), 33, 2),
 }
 
 

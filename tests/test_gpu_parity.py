@@ -513,7 +513,7 @@ def make_edm(cfg, sd, dev, max_batch=None):
     return net.to(dev).eval()
 
 
-@pytest.mark.parametrize("name", ["edm_mini", "edm_mini_cond", "edm_ffhq"])
+@pytest.mark.parametrize("name", ["edm_mini", "edm_mini_cond", "edm_ffhq", "edm_attn32"])
 def test_edm_forward_vs_reference_fixture(dev, name):
     """DhariwalUNet (models/EDM.py) through lfm_create_edm vs outputs of the reference's own module: vector and 0-d t,
     labels, forward_with_cfg (drop_half_label), both attention kernels (256-token tcgen05 / short-grid SIMT), the
@@ -613,12 +613,12 @@ def test_edm_imnet_preset_full_size_properties(dev):
 
 
 def test_edm_unsupported_configuration_fails_loudly(dev):
-    """Self-attention on a 32x32 grid (1024 tokens) has no native kernel: lfm_create_edm must refuse (and release the
+    """Self-attention on a 64x64 grid (4096 tokens) has no native kernel: lfm_create_edm must refuse (and release the
     half-built context), never fall back; a supported network created afterwards works."""
-    net = lfm_b200.DhariwalUNet(img_resolution=32, in_channels=4, out_channels=4, model_channels=128, channel_mult=(1, 2),
-                                num_blocks=1, attn_resolutions=(32,)).to(dev)
+    net = lfm_b200.DhariwalUNet(img_resolution=64, in_channels=4, out_channels=4, model_channels=128, channel_mult=(1, 2),
+                                num_blocks=1, attn_resolutions=(64,)).to(dev)
     with pytest.raises(RuntimeError, match="not supported"):
-        net(torch.tensor(0.5, device=dev), torch.randn(1, 4, 32, 32, device=dev))
+        net(torch.tensor(0.5, device=dev), torch.randn(1, 4, 64, 64, device=dev))
     ok = lfm_b200.DhariwalUNet(img_resolution=16, in_channels=4, out_channels=4, model_channels=128, channel_mult=(1, 2),
                                num_blocks=1, attn_resolutions=(8,)).to(dev)
     v = ok(torch.tensor(0.5, device=dev), torch.randn(2, 4, 16, 16, device=dev))

@@ -16,7 +16,7 @@ def edm_cfg_from_golden(g):
                           attn_resolutions=tuple(int(v) for v in g["cfg_attn_resolutions"]))
 
 
-@pytest.mark.parametrize("name", ["edm_mini", "edm_mini_cond"])
+@pytest.mark.parametrize("name", ["edm_mini", "edm_mini_cond", "edm_attn32"])
 def test_edm_forward_matches_reference(name):
     g = load_golden(name)
     cfg = edm_cfg_from_golden(g)
