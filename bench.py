@@ -11,7 +11,7 @@ sampling pass over one batch of 64 latents per GPU.  Metric: images/s (whole job
 
 After the headline region the same process also measures, and reports under extra keys of the SAME line:
 `other_configs` (BASELINE.json configs 3, 4, 5 at this GPU count: DiT-B/2 CFG Heun-25, ADM UNet dopri5 1e-5 at N=1,
-DiT-L/2 batch-128 Euler sweep in weak and strong scaling), `gemm_vs_cublas` (the four DiT-L GEMM shapes, our kernel
+DiT-L/2 batch-128 Euler sweep in weak and strong scaling; at N=1 also DiT-XL/2 and DiT-L/2 on 64x64 latents), `gemm_vs_cublas` (the four DiT-L GEMM shapes, our kernel
 vs torch.matmul on the same box), `gpu_eager_baseline` (the reference network in eager PyTorch on this GPU: bf16
 autocast + SDPA + TF32) and `decode` (images/s including the native VAE decode).  `--no-extras` skips them.
 
