@@ -172,12 +172,18 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
     static const int split_env = env_int("LFM_GEMM_SPLIT", 1);
     const bool can_split = tbh != nullptr && split_env != 0;
     static const int halves_env = env_int("LFM_GEMM_HALVES", 1);  // A/B switch of the tile-starved mode below
-    if (starved_halves && halves_env && can_split && ksplit == 1 && 2 * tiles <= clusters)
-        clusters = 2 * tiles;  // tile-starved launch: one CTA pair per 256 x 128 half tile (the kernel sees 2 * tiles <= clusters)
-    else if (tiles < clusters)
+    // Launches of at most ONE wave of tiles (small sampling batches; M = 4096 gives the residual GEMMs 64 tiles for 74 CTA pairs) run
+    // entirely in 256 x 128 half tiles (allow_split = 2): twice the work items, so more pairs are busy when tiles are scarce, and a
+    // pair that gets two halves drains the first one under the second one's mainloop instead of exposing a whole tile's epilogue.
+    int allow = can_split ? 1 : 0;
+    if (starved_halves && halves_env && can_split && ksplit == 1 && tiles <= clusters) {
+        allow = 2;
+        clusters = std::min(2 * tiles, clusters);
+    } else if (tiles < clusters) {
         clusters = tiles;
+    }
     return launch_k(kern, dim3(2 * clusters), kG2Threads, kG2SmemBytes, s, ta, tb, tout, tbh != nullptr ? *tbh : tb, M, N, K, ep, cg,
-                    can_split ? 1 : 0, ksplit, split_row_pitch);
+                    allow, ksplit, split_row_pitch);
 }
 
 // Pair kernel with the LayerNorm finisher (ep.ln_out != nullptr; N == D): see GemmEpi::rb_count
