@@ -382,10 +382,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a,   // A [M, K], bo
             full_count = num_tiles - rem;
             num_items = full_count + 2 * rem;
         } else if (allow_split == 2) {
-            // at most one wave of tiles (small batches: 256 token rows give fc2 four tiles for 74 CTA pairs, 4096 rows 64): EVERY
-            // tile is cut into its two 256 x 128 halves - twice the SMs work when tiles are scarce, the serial K loop of an item takes
-            // half the time, and a pair with two halves drains the first under the second's mainloop.  Same accumulation order per
-            // element as the full-width tile: results are bit-identical.
+            // tile-starved launch (the host sets 2 when 2 x tiles <= CTA pairs; small batches: 256 token rows give fc2 four tiles for
+            // 74 CTA pairs): EVERY tile is cut into its two 256 x 128 halves, twice the SMs work and the serial K loop of an item takes
+            // half the time.  Same accumulation order per element as the full-width tile: results are bit-identical.
             full_count = 0;
             num_items = 2 * num_tiles;
         }

@@ -172,13 +172,14 @@ static cudaError_t launch_gemm2_inst(cudaStream_t s, const CUtensorMap& ta, cons
     static const int split_env = env_int("LFM_GEMM_SPLIT", 1);
     const bool can_split = tbh != nullptr && split_env != 0;
     static const int halves_env = env_int("LFM_GEMM_HALVES", 1);  // A/B switch of the tile-starved mode below
-    // Launches of at most ONE wave of tiles (small sampling batches; M = 4096 gives the residual GEMMs 64 tiles for 74 CTA pairs) run
-    // entirely in 256 x 128 half tiles (allow_split = 2): twice the work items, so more pairs are busy when tiles are scarce, and a
-    // pair that gets two halves drains the first one under the second one's mainloop instead of exposing a whole tile's epilogue.
+    // Tile-starved launches (2 x tiles <= CTA pairs; small sampling batches) run entirely in 256 x 128 half tiles (allow_split = 2).
+    // Measured limit of the rule (r3j): extending it to every launch of at most one wave (tiles <= CTA pairs, e.g. the 64 tiles of the
+    // residual GEMMs at 4096 token rows) is SLOWER, 3.66 vs 3.29 ms per evaluation at batch 16 - an N = 128 MMA moves the same A
+    // operand through shared memory as an N = 256 one, so two half tiles cost more than one tile and the hidden epilogue does not pay for it.
     int allow = can_split ? 1 : 0;
-    if (starved_halves && halves_env && can_split && ksplit == 1 && tiles <= clusters) {
+    if (starved_halves && halves_env && can_split && ksplit == 1 && 2 * tiles <= clusters) {
         allow = 2;
-        clusters = std::min(2 * tiles, clusters);
+        clusters = 2 * tiles;
     } else if (tiles < clusters) {
         clusters = tiles;
     }
