@@ -47,6 +47,35 @@ def test_every_dit_models_entry_has_the_reference_key_table():
             assert got == want and list(got) == list(want), (name, side)
 
 
+def test_padded_head_major_attention_layout_is_equivalent():
+    """The layout contract of the mma.sync attention kernels (csrc/kernels.cuh dit_qkv_*_repack_kernel / dit_proj_weight_pad_kernel,
+    restated here): qkv rows re-ordered head-major with head_dim 72 zero-padded to 80, proj columns padded to match.  Attention computed
+    in that layout (scale 72^-1/2) followed by the padded projection equals timm's Attention on the original weights."""
+    D, H, dh, dhp, T, B = 1152, 16, 72, 80, 16, 2
+    g = torch.Generator().manual_seed(5)
+    wq, bq = torch.randn(3 * D, D, generator=g) * 0.03, torch.randn(3 * D, generator=g) * 0.1
+    wp, bp = torch.randn(D, D, generator=g) * 0.03, torch.randn(D, generator=g) * 0.1
+    x = torch.randn(B, T, D, generator=g)
+    cfg = odit.DiTConfig(hidden_size=D, depth=1, num_heads=H)
+    want = odit.attention({"a.qkv.weight": wq, "a.qkv.bias": bq, "a.proj.weight": wp, "a.proj.bias": bp}, "a.", cfg, x)
+    # destination row r = head * 3 dhp + which * dhp + d  <-  source row which * D + head * dh + d  (zero for d >= dh)
+    r = torch.arange(3 * H * dhp)
+    h, which, d = r // (3 * dhp), (r % (3 * dhp)) // dhp, r % dhp
+    src = (which * D + h * dh + d).clamp(max=3 * D - 1)
+    live = (d < dh)
+    wq2 = torch.where(live[:, None], wq[src], torch.zeros(()))
+    bq2 = torch.where(live, bq[src], torch.zeros(()))
+    # destination column c = head * dhp + d  <-  source column head * dh + d
+    c = torch.arange(H * dhp)
+    hc, dc = c // dhp, c % dhp
+    wp2 = torch.where((dc < dh)[None, :], wp[:, (hc * dh + dc).clamp(max=D - 1)], torch.zeros(()))
+    qkv = (x @ wq2.T + bq2).reshape(B, T, H, 3, dhp).permute(3, 0, 2, 1, 4)     # [3, B, H, T, dhp]
+    o = torch.softmax((qkv[0] @ qkv[1].transpose(-1, -2)) * dh ** -0.5, dim=-1) @ qkv[2]
+    assert float(o[..., dh:].abs().max()) == 0.0                                 # padded output channels are exactly zero
+    got = o.transpose(1, 2).reshape(B, T, H * dhp) @ wp2.T + bp
+    assert float((got - want).norm() / want.norm()) < 1e-5
+
+
 def test_reference_init_is_degenerate_and_synthetic_is_not():
     net = _mini()
     assert float(net.final_layer.linear.weight.abs().max()) == 0.0          # models/DiT.py:225-228
@@ -98,6 +127,13 @@ def test_create_network_factory():
     with torch.device("meta"):
         net = lfm_b200.create_network(cfg)
     assert net.hidden_size == 768 and net.depth == 12 and net.table_rows == 1001 and net.img_resolution == 32
+    # --model_type DiT-XL/2 --image_size 512: head_dim 72 on 64 x 64 latents (1024 tokens) - models/__init__.py:6-17 maps it the same way
+    cfg = types.SimpleNamespace(use_origin_adm=False, model_type="DiT-XL/2", image_size=512, f=8, num_in_channels=4,
+                                label_dropout=0.0, num_classes=1)
+    with torch.device("meta"):
+        net = lfm_b200.create_network(cfg)
+    assert (net.hidden_size, net.depth, net.num_heads, net.patch_size, net.img_resolution, net.table_rows) == (1152, 28, 16, 2, 64, 1)
+    assert tuple(net.pos_embed.shape) == (1, 1024, 1152)
 
 
 def test_ddp_index_helpers():
