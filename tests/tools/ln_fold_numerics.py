@@ -6,13 +6,13 @@
 Today the GEMM's A operand is bf16(LN(x) * (1 + scale) + shift); the folded form would feed bf16(x * (1 + scale)) - no mean subtraction before the
 rounding - and apply r, mu in the epilogue.  This script measures both roundings against the fp32 result on the token stream of a synthetic
 DiT-L/2 (oracle weights), block by block, to see whether the folded form loses accuracy when |mean| is not small against the row's spread.
-usage: python scripts/ln_fold_numerics.py [blocks]"""
+usage: python tests/tools/ln_fold_numerics.py [blocks]"""
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import dit as odit  # noqa: E402  (analysis script: not part of the product path)
 
