@@ -49,6 +49,7 @@ def test_cli_builds_every_native_network_family():
               "--synthetic_init", "3", "--no_decode"]
     cases = [
         (["--model_type", "DiT-S/2", "--num_classes", "1", "--label_dropout", "0."], DiT),
+        (["--model_type", "DiT-S/8", "--num_classes", "10", "--label_dropout", "0.1"], DiT),   # 4 x 4 token grid
         (["--model_type", "adm", "--use_origin_adm", "--ch_mult", "1", "2", "--attn_resolutions", "2", "--num_res_blocks", "1",
           "--num_heads", "2"], UNetModel),
         (["--model_type", "adm", "--ch_mult", "1", "2", "--attn_resolutions", "16", "--num_res_blocks", "1", "--label_dim", "7"],
